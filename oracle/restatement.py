@@ -26,6 +26,8 @@ Plain numpy, explicit equations; ``dtype`` selects fp32 or fp
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 LN_EPS = 1e-5
@@ -130,17 +132,42 @@ def fitb(query, cand):
     return d.argmin(-1).astype(np.int64), d
 
 
+_LIB = None
+
+
+def _search_lib():
+    """oracle/search_oracle.c through ctypes (built on first use by oracle/Makefile)."""
+    global _LIB
+    if _LIB is None:
+        import ctypes
+        import os
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        so = os.path.join(here, "_build", "liboracle_search.so")
+        src = os.path.join(here, "search_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", here])
+        lib = ctypes.CDLL(so)
+        i64, vp = ctypes.c_int64, ctypes.c_void_p
+        lib.ofx_oracle_scores.argtypes = [vp, i64, vp, i64, i64, ctypes.c_int, vp]
+        lib.ofx_oracle_search.argtypes = [vp, i64, vp, i64, i64, ctypes.c_int, i64, i64, ctypes.c_int, vp, vp]
+        lib.ofx_oracle_scores.restype = lib.ofx_oracle_search.restype = None
+        _LIB = lib
+    return _LIB
+
+
+_METRIC = {"dot": 0, "l2": 1}
+
+
 def search_scores(queries, gallery, metric="l2"):
     """fp64 ranking score, larger = better.  'l2': q.g - 0.5|g|^2 (same order as -cdist,
-    SURVEY.md D8); 'dot': q.g."""
-    q = np.asarray(queries, np.float64)
-    g = np.asarray(gallery, np.float64)
-    s = q @ g.T
-    if metric == "l2":
-        s = s - 0.5 * (g * g).sum(-1)[None, :]
-    elif metric != "dot":
-        raise ValueError(metric)
-    return s
+    SURVEY.md D8); 'dot': q.g.  Position-independent sequential fp64 sums (search_oracle.c)."""
+    q = np.ascontiguousarray(queries, np.float32)
+    g = np.ascontiguousarray(gallery, np.float32)
+    out = np.empty((len(q), len(g)), np.float64)
+    _search_lib().ofx_oracle_scores(q.ctypes.data, len(q), g.ctypes.data, len(g), q.shape[1],
+                                    _METRIC[metric], out.ctypes.data)
+    return out
 
 
 def topk_lex(scores, k, id_offset=0):
@@ -150,17 +177,18 @@ def topk_lex(scores, k, id_offset=0):
     return order.astype(np.int64) + id_offset, np.take_along_axis(scores, order, -1)
 
 
-def search(queries, gallery, k=10, metric="l2", chunk=65536):
-    """Exact k-NN of complementary_item_retrieval_trainer.py:240-242 restated as a chunked
-    fp64 max-score search with deterministic tie-break.  Returns (idx (nq,k) i64, score)."""
-    nq = len(queries)
-    best_i = np.zeros((nq, 0), np.int64)
-    best_s = np.zeros((nq, 0), np.float64)
-    for lo in range(0, len(gallery), chunk):
-        s = search_scores(queries, gallery[lo:lo + chunk], metric)
-        i, s = topk_lex(s, min(k, s.shape[1]), lo)
-        best_i, best_s = merge_topk(np.concatenate([best_i, i], 1), np.concatenate([best_s, s], 1), k)
-    return best_i, best_s
+def search(queries, gallery, k=10, metric="l2", id_offset=0):
+    """Exact k-NN of complementary_item_retrieval_trainer.py:240-242 restated as an fp64
+    max-score search with deterministic tie-break.  Returns (idx (nq,k) i64, score f64)."""
+    q = np.ascontiguousarray(queries, np.float32)
+    g = np.ascontiguousarray(gallery, np.float32)
+    idx = np.empty((len(q), k), np.int64)
+    score = np.empty((len(q), k), np.float64)
+    _search_lib().ofx_oracle_search(q.ctypes.data, len(q), g.ctypes.data, len(g), q.shape[1],
+                                    _METRIC[metric], k, id_offset, os.cpu_count() or 1,
+                                    idx.ctypes.data,
+                                    score.ctypes.data)
+    return idx, score
 
 
 def merge_topk(idx, score, k):

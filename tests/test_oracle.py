@@ -76,7 +76,7 @@ def test_search_oracle_matches_reference_idiom(golden_dir):
     pool = synth.make_items(3000, 512, seed=int(g["pool_seed"]))
     q = synth.make_queries(64, 1024, seed=int(g["query_seed"])) * np.float32(0.05)
     assert digest(pool, q) == str(g["input_digest"])
-    idx, score = R.search(q, pool, k=50, metric="l2", chunk=1000)
+    idx, score = R.search(q, pool, k=50, metric="l2")
     # |g|^2 == 2 for every item, so dot and l2 rankings coincide
     idx_dot, _ = R.search(q, pool, k=50, metric="dot")
     assert np.array_equal(idx, idx_dot)
@@ -98,7 +98,7 @@ def test_topk_tie_break_lowest_index():
     assert idx.tolist() == [[1, 2, 3]]  # torch.topk gives [3,5,1] here
     gal = synth.make_items(500, 512, seed=9, dup=50)
     q = synth.make_queries(8, 1024, seed=10)
-    idx, score = R.search(q, gal, k=20, chunk=128)
+    idx, score = R.search(q, gal, k=20)
     full_i, full_s = R.topk_lex(R.search_scores(q, gal), 20)
     assert np.array_equal(idx, full_i)
     for r in range(8):  # equal scores -> ascending index
