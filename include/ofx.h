@@ -1,0 +1,178 @@
+/* libofx.so -- C ABI of the B200-native OutfitX outfit-scoring hot path (sm_100a).
+ *
+ * Every entry point below replaces a piece of the reference's Python path
+ * (/root/reference, cited as file:line).  The reference has no FFI of its own: its "plugin
+ * interface" for this path is the nn.Module API of src/models/outfit_x.py plus three caller
+ * idioms in the trainers / demo.  outfitx_b200/model.py mirrors that Python API and binds
+ * this library with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - plain pointers + sizes, no C++ / torch types; all data pointers are DEVICE pointers
+ *    unless the name says host; tensors are dense row-major.
+ *  - every call returns int: OFX_OK or a negative OFX_E_*; ofx_last_error() gives the
+ *    thread-local message.  No exceptions, no exit().
+ *  - all work is enqueued on the caller's CUDA stream (passed as void* = cudaStream_t);
+ *    no hidden synchronisation, no allocation: scratch memory is a caller-provided
+ *    workspace whose size is queried first.
+ *  - there is no CPU fallback: without an sm_100 device every compute call fails with
+ *    OFX_E_ARCH.
+ */
+#ifndef OFX_H_
+#define OFX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFX_VERSION 100
+
+#if defined(__GNUC__)
+#define OFX_API __attribute__((visibility("default")))
+#else
+#define OFX_API
+#endif
+
+enum {
+    OFX_OK = 0,
+    OFX_E_SHAPE = -1,   /* unsupported / inconsistent shape                    */
+    OFX_E_ARG = -2,     /* null or misaligned pointer, bad enum value          */
+    OFX_E_ARCH = -3,    /* no CUDA device of compute capability 10.x            */
+    OFX_E_CUDA = -4,    /* a CUDA runtime / driver call failed                  */
+    OFX_E_WORKSPACE = -5 /* workspace too small                                 */
+};
+
+/* arithmetic of the hot GEMMs */
+enum {
+    OFX_PREC_BF16 = 0, /* bf16 operands on tcgen05 tensor cores, fp32 accumulate (TMEM)   */
+    OFX_PREC_FP32 = 1  /* fp32 CUDA-core path: the <=1e-3-relative parity mode             */
+};
+
+enum { OFX_TASK_CP = 0, OFX_TASK_CIR = 1 }; /* FITB uses the CIR task (outfit_x.py:86-87) */
+enum { OFX_FUSE_CONCAT = 0, OFX_FUSE_MEAN = 1 };
+enum { OFX_METRIC_DOT = 0, OFX_METRIC_L2 = 1 };
+
+/* Model dimensions: OutfitXConfig / TransformerConfig
+ * (src/models/configs/outfit_x_config.py:8-30, transformer_config.py:7-23). */
+typedef struct ofx_shape {
+    int32_t d_model;   /* 512 (clip+mean), 1024 (clip+concat) or 1536 (slip+concat)         */
+    int32_t d_embed;   /* cir_ffn output = 2*dim_per_modality (outfit_x_config.py:23)        */
+    int32_t n_head;    /* 16                                                                */
+    int32_t n_layers;  /* 6                                                                 */
+    int32_t d_ffn;     /* 2024 (zero-padded to a multiple of 64 inside the packed weights)  */
+    int32_t max_items; /* 16 (outfit_x_config.py:13)                                        */
+    int32_t precision; /* OFX_PREC_*                                                        */
+} ofx_shape;
+
+/* Order of the fp32 parameter pointers handed to ofx_pack_weights: per layer
+ * OFX_W_PER_LAYER tensors in this order, then the OFX_W_GLOBAL model-level ones
+ * (state_dict keys of src/models/outfit_x.py:32-71). */
+enum {
+    OFX_W_IN_PROJ_W = 0, /* self_attn.in_proj_weight (3Dm, Dm) */
+    OFX_W_IN_PROJ_B,     /* self_attn.in_proj_bias   (3Dm)     */
+    OFX_W_OUT_PROJ_W,    /* self_attn.out_proj.weight (Dm, Dm) */
+    OFX_W_OUT_PROJ_B,    /* self_attn.out_proj.bias  (Dm)      */
+    OFX_W_LINEAR1_W,     /* linear1.weight (F, Dm)             */
+    OFX_W_LINEAR1_B,     /* linear1.bias   (F)                 */
+    OFX_W_LINEAR2_W,     /* linear2.weight (Dm, F)             */
+    OFX_W_LINEAR2_B,     /* linear2.bias   (Dm)                */
+    OFX_W_NORM1_W,
+    OFX_W_NORM1_B,
+    OFX_W_NORM2_W,
+    OFX_W_NORM2_B,
+    OFX_W_PER_LAYER
+};
+enum {
+    OFX_G_OUTFIT_TOKEN = 0, /* outfit_token (Dm)             outfit_x.py:53-55 */
+    OFX_G_TARGET_IMG,       /* target_item_image_emb (Dm/2)  outfit_x.py:69-71 */
+    OFX_G_CP_W,             /* cp_ffn.1.weight (1, Dm)       outfit_x.py:57-61 */
+    OFX_G_CP_B,             /* cp_ffn.1.bias (1)                               */
+    OFX_G_CIR_W,            /* cir_ffn.0.weight (De, Dm)     outfit_x.py:65-67 */
+    OFX_W_GLOBAL
+};
+
+OFX_API int ofx_version(void);
+OFX_API const char* ofx_last_error(void);
+/* 0 when cuda device `device` has compute capability 10.x, else OFX_E_ARCH */
+OFX_API int ofx_device_ok(int device);
+
+/* ---- weights: replaces nn.Module parameter storage + load_state_dict (demo/app.py:102-103) */
+OFX_API size_t ofx_packed_weights_bytes(const ofx_shape* shape);
+/* params: HOST array of n_layers*OFX_W_PER_LAYER + OFX_W_GLOBAL DEVICE fp32 pointers */
+OFX_API int ofx_pack_weights(const ofx_shape* shape, const float* const* params, void* packed,
+                     void* stream);
+
+/* ---- fusion: F.normalize per modality + aggregate_embeddings
+ * (src/models/encoders/image/base_image_encoder.py:46-47, text/base_text_encoder.py:37-38,
+ *  src/utils/model_utils.py:26-45).  img, txt: (rows, dpm) fp32 -> out (rows, 2*dpm | dpm). */
+OFX_API int ofx_fuse(const float* img, const float* txt, int64_t rows, int32_t dpm, int32_t mode,
+             int32_t normalize, float* out, void* stream);
+
+/* ---- encoder forward: OutfitX._cp_forward / _cir_forward (outfit_x.py:120-172) plus the
+ * caller idioms sigmoid (compatibility_prediction_trainer.py:408) and FITB cdist->argmin
+ * (fill_in_the_blank_trainer.py:50-53).
+ *
+ * Inputs: either `emb` (B,16,Dm) fused fp32 embeddings (the reference's outfit_embedding), or
+ * raw modalities img/txt (B,16,dpm) fused on the fly (fuse_mode, normalize) with emb == NULL.
+ * mask (B,16) bytes, non-zero = padding (outfit_mask, True = pad).  Valid items may sit in
+ * any slot; padded slots are never read. */
+typedef struct ofx_forward_args {
+    int32_t task;          /* OFX_TASK_*                                              */
+    int32_t batch;         /* B outfits                                               */
+    const float* emb;      /* (B,16,Dm) or NULL                                       */
+    const float* img;      /* (B,16,dpm) or NULL                                      */
+    const float* txt;      /* (B,16,dpm) or NULL                                      */
+    int32_t fuse_mode;     /* OFX_FUSE_* (used with img/txt)                          */
+    int32_t normalize;     /* L2-normalise each modality first (reference: yes)       */
+    const uint8_t* mask;   /* (B,16)                                                  */
+    const float* text;     /* CIR: target_item_text_embedding (B, Dm/2)               */
+    float* logits;         /* CP out: (B) logits  (== reference (B,1))                */
+    float* probs;          /* CP out: (B) sigmoid(logit), may be NULL                 */
+    float* query;          /* CIR out: (B, De) query embeddings                       */
+    const float* cand;     /* FITB: (B, n_cand, De) candidates or NULL                */
+    int32_t n_cand;        /* 4 in the reference                                      */
+    float* fitb_dist;      /* FITB out: (B, n_cand) L2 distances, may be NULL         */
+    int64_t* fitb_argmin;  /* FITB out: (B) first-minimum index                       */
+} ofx_forward_args;
+
+OFX_API size_t ofx_encoder_workspace_bytes(const ofx_shape* shape, int32_t batch);
+OFX_API int ofx_encoder_forward(const ofx_shape* shape, const void* packed_weights,
+                        const ofx_forward_args* args, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ---- CIR search: torch.cdist -> torch.topk(largest=False)
+ * (complementary_item_retrieval_trainer.py:240-242, demo/app.py:189-190), restated as the
+ * arg-max of  q.g - 0.5|g|^2  (OFX_METRIC_L2, same ranking as ascending L2 distance) or of
+ * q.g (OFX_METRIC_DOT); ties are broken by the lowest gallery index. */
+OFX_API size_t ofx_gallery_packed_bytes(int64_t n_rows, int32_t dim);
+/* gallery (n_rows, dim) fp32 -> packed bf16 rows + fp32 0.5|g|^2 (computed from the fp32 data) */
+OFX_API int ofx_gallery_pack(const float* gallery, int64_t n_rows, int32_t dim, void* packed,
+                     void* stream);
+OFX_API size_t ofx_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_query, int32_t k);
+/* Exact top-k of every query over this shard's rows.  Candidates come from a bf16 tcgen05
+ * pass with a fused per-row top-k' selection (the score matrix never reaches HBM); they are
+ * re-scored in fp64 from the fp32 gallery and ranked by (-score, index).  out_idx carries
+ * GLOBAL ids (id_offset + local row); slots beyond n_rows get idx -1 / score -inf. */
+OFX_API int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows, int32_t dim,
+                    int64_t id_offset, const float* queries, int32_t n_query, int32_t k,
+                    int32_t metric, double* out_score, int64_t* out_idx, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* Merge R per-shard lists (R, nq, k) by (-score, idx) into (nq, k): the step after the NCCL
+ * all-gather of the gallery-sharded search (no reference counterpart: its inference is
+ * single-GPU, complementary_item_retrieval_trainer.py:350-351). */
+OFX_API int ofx_topk_merge(const double* scores, const int64_t* idx, int32_t n_lists, int32_t n_query,
+                   int32_t k, double* out_score, int64_t* out_idx, void* stream);
+
+/* ---- building block exported for tests / profiling: C = A . W^T (+bias)(+mish)(+residual)
+ * A (M,K) bf16 pitch lda, W (N,K) bf16 pitch ldw on the tcgen05 pipeline.  out is bf16 or
+ * fp32 (out_f32), pitch ldo; residual fp32 pitch ldr or NULL.  N % 128 == 0, K % 64 == 0. */
+OFX_API int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int32_t m, int32_t n,
+                  int32_t k, const float* bias, int32_t act_mish, const float* residual,
+                  int64_t ldr, void* out, int64_t ldo, int32_t out_f32, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFX_H_ */

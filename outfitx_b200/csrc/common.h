@@ -1,0 +1,46 @@
+// Host-side helpers shared by all translation units of libofx.so: error convention,
+// TMA tensor-map creation, launch helpers.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ofx.h"
+
+namespace ofx {
+
+// thread-local last-error string returned by ofx_last_error()
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+const char* last_error();
+
+#define OFX_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return ::ofx::fail(OFX_E_CUDA, "%s failed: %s (%s:%d)", #expr,                    \
+                               cudaGetErrorString(e__), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define OFX_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != OFX_OK) return rc__; \
+    } while (0)
+
+#define OFX_LAUNCH_CHECK() OFX_CUDA(cudaGetLastError())
+
+// Requires a device of compute capability 10.x (the kernels are sm_100a-only).
+int require_sm100();
+int sm_count();
+
+// 2-D bf16 tensor map: `rows` x `cols` elements, row pitch `ld` elements, box = box_rows x 64
+// elements (128 B) with the 128-byte swizzle the UMMA descriptors expect; OOB reads give zeros.
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                   uint32_t box_rows);
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace ofx

@@ -1,0 +1,510 @@
+// Non-GEMM pieces of the outfit encoder, fused per row / per outfit:
+//   fuse / assemble (normalise + concat|mean + prefix token + drop padded slots),
+//   LayerNorm, the <=17-token masked attention, CP head (+sigmoid), FITB distances.
+// Reference arithmetic: SURVEY.md App. A, i.e. torch.nn.TransformerEncoderLayer's pre-LN
+// slow path as driven by /root/reference/src/models/outfit_x.py:120-172.
+//
+// Token layout in HBM (all activations): rows [0, B) are the prefix tokens of the B outfits,
+// rows [B + off[b], B + off[b+1]) are outfit b's valid items in slot order.  Padded slots are
+// dropped: they are never attended to (key-padding mask = -inf) and only token 0 is read by
+// the heads, so the result is unchanged; the model has no positional
+// encoding, so valid items may come from any slot.
+#include "encoder_ops.h"
+
+namespace ofx {
+
+template <class T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8 consecutive elements (16-byte aligned for bf16, 32-byte for fp32) <-> fp32 registers
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ offsets
+// off[b] = number of valid items in outfits < b; off[B] = total items; n_tok = B + off[B].
+__global__ void __launch_bounds__(1024)
+scan_valid_kernel(const uint8_t* __restrict__ mask, int batch, int max_items, int* __restrict__ off,
+                  int* __restrict__ n_tok) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < batch; base += 1024) {
+        const int b = base + threadIdx.x;
+        int cnt = 0;
+        if (b < batch)
+            for (int j = 0; j < max_items; ++j) cnt += mask[b * max_items + j] == 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane], s = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += u;
+            }
+            warp_tot[lane] = s - t;  // exclusive
+        }
+        __syncthreads();
+        const int excl = carry + warp_tot[warp] + incl - cnt;
+        if (b < batch) off[b] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + cnt;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        off[batch] = carry;
+        *n_tok = batch + carry;
+    }
+}
+
+// ------------------------------------------------------------------ fusion of one item row
+// One warp produces one fused row in registers: lane l holds elements l*4 + 128*i (float4).
+// concat: [img/|img| ; txt/|txt|]  (2*dpm)    mean: (img/|img| + txt/|txt|)/2  (dpm)
+template <int DM>
+__device__ __forceinline__ void load_fused_row(float4 (&v)[DM / 128], const float* img,
+                                               const float* txt, int dpm, int mode, int normalize,
+                                               int lane) {
+    constexpr int NV = DM / 128;
+    if (mode == OFX_FUSE_CONCAT) {
+        // DM = 2*dpm: vectors [0, NV/2) come from img, the rest from txt
+        float si = 0.f, st = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = i * 128 + lane * 4;
+            const bool is_img = e < dpm;
+            v[i] = *reinterpret_cast<const float4*>(is_img ? img + e : txt + (e - dpm));
+            float s = v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+            if (is_img) si += s; else st += s;
+        }
+        if (normalize) {
+            si = 1.f / fmaxf(sqrtf(warp_sum(si)), 1e-12f);
+            st = 1.f / fmaxf(sqrtf(warp_sum(st)), 1e-12f);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float s = (i * 128 + lane * 4 < dpm) ? si : st;
+                v[i].x *= s; v[i].y *= s; v[i].z *= s; v[i].w *= s;
+            }
+        }
+    } else {
+        float4 t[NV];
+        float si = 0.f, st = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = i * 128 + lane * 4;
+            v[i] = *reinterpret_cast<const float4*>(img + e);
+            t[i] = *reinterpret_cast<const float4*>(txt + e);
+            si += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+            st += t[i].x * t[i].x + t[i].y * t[i].y + t[i].z * t[i].z + t[i].w * t[i].w;
+        }
+        float ai = 0.5f, at = 0.5f;
+        if (normalize) {
+            ai = 0.5f / fmaxf(sqrtf(warp_sum(si)), 1e-12f);
+            at = 0.5f / fmaxf(sqrtf(warp_sum(st)), 1e-12f);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i].x = v[i].x * ai + t[i].x * at; v[i].y = v[i].y * ai + t[i].y * at;
+            v[i].z = v[i].z * ai + t[i].z * at; v[i].w = v[i].w * ai + t[i].w * at;
+        }
+    }
+}
+
+// standalone fusion (ofx_fuse): one warp per row
+template <int DM>
+__global__ void __launch_bounds__(256)
+fuse_kernel(const float* __restrict__ img, const float* __restrict__ txt, long long rows, int dpm,
+            int mode, int normalize, float* __restrict__ out) {
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float4 v[DM / 128];
+    load_fused_row<DM>(v, img + row * dpm, txt + row * dpm, dpm, mode, normalize, lane);
+#pragma unroll
+    for (int i = 0; i < DM / 128; ++i)
+        *reinterpret_cast<float4*>(out + row * DM + i * 128 + lane * 4) = v[i];
+}
+
+int fuse_rows(const float* img, const float* txt, long long rows, int dpm, int mode, int normalize,
+              float* out, cudaStream_t stream) {
+    const int dm = mode == OFX_FUSE_CONCAT ? 2 * dpm : dpm;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    if (rows <= 0) return OFX_OK;
+    switch (dm) {
+        case 512: fuse_kernel<512><<<grid, 256, 0, stream>>>(img, txt, rows, dpm, mode, normalize, out); break;
+        case 1024: fuse_kernel<1024><<<grid, 256, 0, stream>>>(img, txt, rows, dpm, mode, normalize, out); break;
+        case 1536: fuse_kernel<1536><<<grid, 256, 0, stream>>>(img, txt, rows, dpm, mode, normalize, out); break;
+        default: return fail(OFX_E_SHAPE, "ofx_fuse: fused width %d not in {512,1024,1536}", dm);
+    }
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+// ------------------------------------------------------------------ LayerNorm of a row held
+// in registers (two-pass in registers: mean, then biased variance), eps = 1e-5.
+template <int DM, class T>
+__device__ __forceinline__ void ln_store(const float4 (&v)[DM / 128], const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, T* __restrict__ out, int lane) {
+    constexpr int NV = DM / 128;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+    const float mu = warp_sum(s) * (1.f / DM);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+        q += a * a + b * b + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / DM) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int e = i * 128 + lane * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + e));
+        float y0 = (v[i].x - mu) * rstd * g.x + b.x, y1 = (v[i].y - mu) * rstd * g.y + b.y;
+        float y2 = (v[i].z - mu) * rstd * g.z + b.z, y3 = (v[i].w - mu) * rstd * g.w + b.w;
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(out + e) = make_float4(y0, y1, y2, y3);
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0);
+            u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(out + e) = u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ assemble (+ LayerNorm 1 of layer 0)
+// One warp per (outfit, slot): slot 0 = prefix token (outfit_token | [target_img ; text]),
+// slot s>0 = item s-1.  Writes the fp32 residual stream x and h = LN1_0(x).
+template <int DM, class T>
+__global__ void __launch_bounds__(256)
+assemble_kernel(AssembleArgs a, float* __restrict__ x, T* __restrict__ h) {
+    const long long gw = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int slots = a.max_items + 1;
+    const int b = static_cast<int>(gw / slots), s = static_cast<int>(gw % slots);
+    if (b >= a.batch) return;
+    const int lane = threadIdx.x & 31;
+    constexpr int NV = DM / 128;
+    float4 v[NV];
+    long long row;
+    if (s == 0) {
+        row = b;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = i * 128 + lane * 4;
+            if (a.task == OFX_TASK_CP) v[i] = __ldg(reinterpret_cast<const float4*>(a.outfit_token + e));
+            else if (e < DM / 2) v[i] = __ldg(reinterpret_cast<const float4*>(a.target_img + e));
+            else v[i] = *reinterpret_cast<const float4*>(a.text + static_cast<long long>(b) * (DM / 2) + (e - DM / 2));
+        }
+    } else {
+        const uint8_t* m = a.mask + static_cast<long long>(b) * a.max_items;
+        if (m[s - 1]) return;  // padded slot: dropped
+        int rank = 0;
+        for (int j = 0; j < s - 1; ++j) rank += m[j] == 0;
+        row = a.batch + a.off[b] + rank;
+        const long long item = static_cast<long long>(b) * a.max_items + (s - 1);
+        if (a.emb) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                v[i] = *reinterpret_cast<const float4*>(a.emb + item * DM + i * 128 + lane * 4);
+        } else {
+            load_fused_row<DM>(v, a.img + item * a.dpm, a.txt + item * a.dpm, a.dpm, a.fuse_mode,
+                               a.normalize, lane);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(x + row * DM + i * 128 + lane * 4) = v[i];
+    ln_store<DM, T>(v, a.ln_w, a.ln_b, h + row * DM, lane);
+}
+
+template <class T>
+int assemble(const AssembleArgs& a, int dm, float* x, T* h, cudaStream_t stream) {
+    const long long warps = static_cast<long long>(a.batch) * (a.max_items + 1);
+    const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
+    switch (dm) {
+        case 512: assemble_kernel<512, T><<<grid, 256, 0, stream>>>(a, x, h); break;
+        case 1024: assemble_kernel<1024, T><<<grid, 256, 0, stream>>>(a, x, h); break;
+        case 1536: assemble_kernel<1536, T><<<grid, 256, 0, stream>>>(a, x, h); break;
+        default: return fail(OFX_E_SHAPE, "d_model %d not in {512,1024,1536}", dm);
+    }
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+template int assemble<float>(const AssembleArgs&, int, float*, float*, cudaStream_t);
+template int assemble<__nv_bfloat16>(const AssembleArgs&, int, float*, __nv_bfloat16*, cudaStream_t);
+
+int scan_valid(const uint8_t* mask, int batch, int max_items, int* off, int* n_tok, cudaStream_t stream) {
+    scan_valid_kernel<<<1, 1024, 0, stream>>>(mask, batch, max_items, off, n_tok);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+// ------------------------------------------------------------------ LayerNorm: one warp per row
+template <int DM, class T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int rows, const int* __restrict__ rows_dev,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ out) {
+    const int n = rows_dev ? min(*rows_dev, rows) : rows;
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    float4 v[DM / 128];
+#pragma unroll
+    for (int i = 0; i < DM / 128; ++i)
+        v[i] = *reinterpret_cast<const float4*>(x + row * DM + i * 128 + lane * 4);
+    ln_store<DM, T>(v, gamma, beta, out + row * DM, lane);
+}
+
+template <class T>
+int layernorm(const float* x, int rows, const int* rows_dev, int dm, const float* gamma,
+              const float* beta, T* out, cudaStream_t stream) {
+    if (rows <= 0) return OFX_OK;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    switch (dm) {
+        case 512: layernorm_kernel<512, T><<<grid, 256, 0, stream>>>(x, rows, rows_dev, gamma, beta, out); break;
+        case 1024: layernorm_kernel<1024, T><<<grid, 256, 0, stream>>>(x, rows, rows_dev, gamma, beta, out); break;
+        case 1536: layernorm_kernel<1536, T><<<grid, 256, 0, stream>>>(x, rows, rows_dev, gamma, beta, out); break;
+        default: return fail(OFX_E_SHAPE, "d_model %d not in {512,1024,1536}", dm);
+    }
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+template int layernorm<float>(const float*, int, const int*, int, const float*, const float*, float*, cudaStream_t);
+template int layernorm<__nv_bfloat16>(const float*, int, const int*, int, const float*, const float*, __nv_bfloat16*, cudaStream_t);
+
+// ------------------------------------------------------------------ cast rows fp32 -> T
+template <class T>
+__global__ void cast_kernel(const float* __restrict__ in, long long n, T* __restrict__ out) {
+    long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 v = *reinterpret_cast<const float4*>(in + i);
+    out[i] = from_f<T>(v.x); out[i + 1] = from_f<T>(v.y); out[i + 2] = from_f<T>(v.z); out[i + 3] = from_f<T>(v.w);
+}
+template <class T>
+int cast_rows(const float* in, long long n, T* out, cudaStream_t stream) {
+    if (n <= 0) return OFX_OK;
+    cast_kernel<T><<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, stream>>>(in, n, out);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+template int cast_rows<float>(const float*, long long, float*, cudaStream_t);
+template int cast_rows<__nv_bfloat16>(const float*, long long, __nv_bfloat16*, cudaStream_t);
+
+// ------------------------------------------------------------------ attention
+// One warp per (outfit, head).  S = 1 + n_valid <= 17 tokens: K and V head slices are staged
+// in shared memory as fp32; lane i owns query i (scores, softmax and the output row live in
+// its registers); softmax over the S keys only -- dropped pads are exactly the -inf keys of
+// the reference's float mask.  row0_only: the pruned last layer (query = prefix token only).
+template <int HD> struct AttnCfg { static constexpr int kWarps = HD > 64 ? 2 : 4; };
+
+template <int HD, class T>
+__global__ void __launch_bounds__(32 * AttnCfg<HD>::kWarps)
+attention_kernel(AttnArgs a) {
+    constexpr int kMaxS = 17;
+    constexpr int kWarps = AttnCfg<HD>::kWarps;
+    __shared__ float s_k[kWarps][kMaxS][HD + 1];
+    __shared__ float s_v[kWarps][kMaxS][HD + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = static_cast<long long>(blockIdx.x) * kWarps + warp;
+    const int b = static_cast<int>(gw / a.n_head), head = static_cast<int>(gw % a.n_head);
+    if (b >= a.batch) return;
+    const int base = a.batch + a.off[b];
+    const int S = 1 + (a.off[b + 1] - a.off[b]);
+    const T* kp = static_cast<const T*>(a.k);
+    const T* vp = static_cast<const T*>(a.v);
+    const T* qp = static_cast<const T*>(a.q);
+    T* op = static_cast<T*>(a.out);
+    // stage K, V: each lane moves 8-element (16 B bf16) pieces of the head slices
+    constexpr int kPieces = HD / 8;
+    for (int c = lane; c < S * kPieces; c += 32) {
+        const int j = c / kPieces, d = (c % kPieces) * 8;
+        const long long r = j == 0 ? b : base + j - 1;
+        float t[8];
+        load8(kp + r * a.ldk + head * HD + d, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_k[warp][j][d + i] = t[i];
+        load8(vp + r * a.ldv + head * HD + d, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_v[warp][j][d + i] = t[i];
+    }
+    __syncwarp();
+    const int nq = a.row0_only ? 1 : S;
+    if (lane >= nq) return;
+    const long long qr = lane == 0 ? b : base + lane - 1;
+    float sc[kMaxS];
+#pragma unroll
+    for (int j = 0; j < kMaxS; ++j) sc[j] = 0.f;
+    // scores: q is streamed from global in chunks of 8 (own row, contiguous)
+    for (int d0 = 0; d0 < HD; d0 += 8) {
+        float q[8];
+        load8(qp + qr * a.ldq + head * HD + d0, q);
+#pragma unroll
+        for (int j = 0; j < kMaxS; ++j) {
+            if (j < S) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sc[j] = fmaf(q[i], s_k[warp][j][d0 + i], sc[j]);
+            }
+        }
+    }
+    const float scale = rsqrtf(static_cast<float>(HD));
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMaxS; ++j) if (j < S) { sc[j] *= scale; mx = fmaxf(mx, sc[j]); }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxS; ++j) if (j < S) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
+    const float inv = 1.f / den;
+    const long long orow = a.row0_only ? b : qr;
+    for (int d0 = 0; d0 < HD; d0 += 8) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxS; ++j) {
+            if (j < S) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = fmaf(sc[j], s_v[warp][j][d0 + i], o[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= inv;
+        store8(op + orow * a.ldo + head * HD + d0, o);
+    }
+}
+
+template <class T>
+int attention(const AttnArgs& a, int head_dim, cudaStream_t stream) {
+    if (a.batch <= 0) return OFX_OK;
+    const long long warps = static_cast<long long>(a.batch) * a.n_head;
+    switch (head_dim) {
+        case 32: attention_kernel<32, T><<<static_cast<unsigned>((warps + 3) / 4), 128, 0, stream>>>(a); break;
+        case 64: attention_kernel<64, T><<<static_cast<unsigned>((warps + 3) / 4), 128, 0, stream>>>(a); break;
+        case 96: attention_kernel<96, T><<<static_cast<unsigned>((warps + 1) / 2), 64, 0, stream>>>(a); break;
+        default: return fail(OFX_E_SHAPE, "head_dim %d not in {32,64,96}", head_dim);
+    }
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+template int attention<float>(const AttnArgs&, int, cudaStream_t);
+template int attention<__nv_bfloat16>(const AttnArgs&, int, cudaStream_t);
+
+// ------------------------------------------------------------------ CP head: warp per outfit
+__global__ void __launch_bounds__(256)
+cp_head_kernel(const float* __restrict__ x0, int batch, int dm, const float* __restrict__ w,
+               const float* __restrict__ bias, float* __restrict__ logits, float* __restrict__ probs) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int e = lane * 4; e < dm; e += 128) {
+        float4 xv = *reinterpret_cast<const float4*>(x0 + static_cast<long long>(b) * dm + e);
+        float4 wv = __ldg(reinterpret_cast<const float4*>(w + e));
+        s += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float z = s + bias[0];
+        logits[b] = z;
+        if (probs) probs[b] = 1.f / (1.f + expf(-z));
+    }
+}
+int cp_head(const float* x0, int batch, int dm, const float* w, const float* bias, float* logits,
+            float* probs, cudaStream_t stream) {
+    if (batch <= 0) return OFX_OK;
+    cp_head_kernel<<<(batch + 7) / 8, 256, 0, stream>>>(x0, batch, dm, w, bias, logits, probs);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+// ------------------------------------------------------------------ FITB: warp per outfit
+// d_j = || q - c_j ||_2 (direct differences, like torch.cdist for small inputs), argmin = first minimum
+__global__ void __launch_bounds__(256)
+fitb_kernel(const float* __restrict__ query, const float* __restrict__ cand, int batch, int n_cand,
+            int de, float* __restrict__ dist, long long* __restrict__ argmin) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    const int lane = threadIdx.x & 31;
+    float best = INFINITY;
+    int best_j = 0;
+    for (int j = 0; j < n_cand; ++j) {
+        const float* c = cand + (static_cast<long long>(b) * n_cand + j) * de;
+        float s = 0.f;
+        for (int e = lane * 4; e < de; e += 128) {
+            float4 qv = *reinterpret_cast<const float4*>(query + static_cast<long long>(b) * de + e);
+            float4 cv = *reinterpret_cast<const float4*>(c + e);
+            float d0 = qv.x - cv.x, d1 = qv.y - cv.y, d2 = qv.z - cv.z, d3 = qv.w - cv.w;
+            s += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+        const float d = sqrtf(warp_sum(s));
+        if (lane == 0 && dist) dist[static_cast<long long>(b) * n_cand + j] = d;
+        if (d < best) { best = d; best_j = j; }
+    }
+    if (lane == 0 && argmin) argmin[b] = best_j;
+}
+int fitb(const float* query, const float* cand, int batch, int n_cand, int de, float* dist,
+         long long* argmin, cudaStream_t stream) {
+    if (batch <= 0) return OFX_OK;
+    fitb_kernel<<<(batch + 7) / 8, 256, 0, stream>>>(query, cand, batch, n_cand, de, dist, argmin);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+// ------------------------------------------------------------------ weight packing
+template <class T>
+__global__ void pack_matrix_kernel(const float* __restrict__ src, int rows, int cols, T* __restrict__ dst,
+                                   int prow, int pcol) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(prow) * pcol) return;
+    const int r = static_cast<int>(i / pcol), c = static_cast<int>(i % pcol);
+    dst[i] = from_f<T>((r < rows && c < cols) ? src[static_cast<long long>(r) * cols + c] : 0.f);
+}
+template <class T>
+int pack_matrix(const float* src, int rows, int cols, T* dst, int prow, int pcol, cudaStream_t stream) {
+    const long long n = static_cast<long long>(prow) * pcol;
+    pack_matrix_kernel<T><<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, rows, cols, dst, prow, pcol);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+template int pack_matrix<float>(const float*, int, int, float*, int, int, cudaStream_t);
+template int pack_matrix<__nv_bfloat16>(const float*, int, int, __nv_bfloat16*, int, int, cudaStream_t);
+
+}  // namespace ofx

@@ -1,0 +1,45 @@
+#pragma once
+#include "common.h"
+
+namespace ofx {
+
+struct AssembleArgs {
+    int task, batch, max_items;
+    const float* emb;      // (B,16,Dm) fused, or null
+    const float* img;      // (B,16,dpm)
+    const float* txt;
+    int dpm, fuse_mode, normalize;
+    const uint8_t* mask;   // (B,16) non-zero = pad
+    const int* off;        // (B+1) exclusive prefix of valid counts
+    const float* outfit_token;  // (Dm)
+    const float* target_img;    // (Dm/2)
+    const float* text;          // (B, Dm/2)
+    const float* ln_w;          // LayerNorm 1 of layer 0 (fused here)
+    const float* ln_b;
+};
+
+struct AttnArgs {
+    int batch, n_head, row0_only;
+    const int* off;
+    const void* q; long long ldq;   // element pitches
+    const void* k; long long ldk;
+    const void* v; long long ldv;
+    void* out; long long ldo;
+};
+
+int scan_valid(const uint8_t* mask, int batch, int max_items, int* off, int* n_tok, cudaStream_t stream);
+int fuse_rows(const float* img, const float* txt, long long rows, int dpm, int mode, int normalize,
+              float* out, cudaStream_t stream);
+template <class T> int assemble(const AssembleArgs& a, int dm, float* x, T* h, cudaStream_t stream);
+template <class T> int layernorm(const float* x, int rows, const int* rows_dev, int dm, const float* gamma,
+                                 const float* beta, T* out, cudaStream_t stream);
+template <class T> int cast_rows(const float* in, long long n, T* out, cudaStream_t stream);
+template <class T> int attention(const AttnArgs& a, int head_dim, cudaStream_t stream);
+int cp_head(const float* x0, int batch, int dm, const float* w, const float* bias, float* logits,
+            float* probs, cudaStream_t stream);
+int fitb(const float* query, const float* cand, int batch, int n_cand, int de, float* dist,
+         long long* argmin, cudaStream_t stream);
+template <class T> int pack_matrix(const float* src, int rows, int cols, T* dst, int prow, int pcol,
+                                   cudaStream_t stream);
+
+}  // namespace ofx

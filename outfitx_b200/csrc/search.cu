@@ -1,0 +1,567 @@
+// CIR search: exact top-k of every query over a gallery shard, behind ofx_topk_search.
+//
+// Replaces the trainer / demo idiom  torch.cdist(Q, G) -> torch.topk(k, largest=False)
+// (/root/reference/src/trains/trainers/complementary_item_retrieval_trainer.py:240-242,
+//  src/demo/app.py:189-190), restated as the arg-max of  q.g - 0.5|g|^2  (or q.g).
+//
+// Pass 1 (tc_pipeline.cuh, tcgen05 / TMEM / TMA): bf16 Q x G^T tiles of 128 queries x 256
+//   gallery rows; the epilogue thread that owns a query row scans the tile straight out of
+//   TMEM and keeps that query's running top-K' in shared memory, so the score matrix never
+//   reaches HBM.  Work is cut into units = (query block, gallery segment); a unit's list lives
+//   on chip for the whole segment sweep and is flushed once.  A per-query global threshold
+//   (the best "K'-th best" any finished unit has seen) lets later units reject almost every
+//   score with one compare.
+// Pass 2: per query, merge the units' lists by (score desc, index asc), re-score the K' best
+//   in fp64 from the fp32 queries / gallery, rank by (-score, index), emit the top k.
+#include "common.h"
+#include "tc_pipeline.cuh"
+
+namespace ofx {
+
+constexpr int kSearchBN = 256;
+constexpr int kMaxSegments = 64;
+
+// order-preserving float <-> uint32 map (for atomicMax on scores); 0 is below every float
+__device__ __forceinline__ uint32_t enc_score(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_score(uint32_t e) {
+    if (e == 0) return -INFINITY;
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e);
+}
+// smallest float strictly greater than x (x finite)
+__device__ __forceinline__ float next_up(float x) {
+    if (x == 0.f) return __uint_as_float(1u);
+    const int b = __float_as_int(x);
+    return __int_as_float(x > 0.f ? b + 1 : b - 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// Unit schedule.  Units u = seg * n_qblocks + qb, CTA c runs units c, c + P, c + 2P, ...
+// Units of one segment share their gallery tiles, and all CTAs sweep a segment's tiles in the
+// same order at the same pace, so every gallery tile is fetched from HBM once and then hit in
+// L2 by the other query blocks.
+// ---------------------------------------------------------------------------------------
+struct SchedSearch {
+    struct Params {
+        int n_qblocks, n_tiles, seg_tiles, n_units;
+    };
+    int m0, n0, unit, cur, tile_hi, step;
+    bool first, last;
+    Params p;
+    __device__ SchedSearch(const Params& pp, int cta, int n_cta) : p(pp) {
+        unit = cta - n_cta;
+        step = n_cta;
+        cur = 0;
+        tile_hi = 0;
+        m0 = n0 = 0;
+        first = last = false;
+    }
+    __device__ bool next() {
+        if (cur + 1 < tile_hi) {
+            ++cur;
+            first = false;
+        } else {
+            unit += step;
+            if (unit >= p.n_units) return false;
+            const int seg = unit / p.n_qblocks;
+            m0 = (unit - seg * p.n_qblocks) * kBM;
+            cur = seg * p.seg_tiles;
+            tile_hi = min(p.n_tiles, cur + p.seg_tiles);
+            first = true;
+        }
+        last = cur + 1 == tile_hi;
+        n0 = cur * kSearchBN;
+        return true;
+    }
+};
+
+struct SearchPlan {
+    int n_qblocks, n_tiles, n_seg, seg_tiles, n_units, grid;
+};
+
+// Pick the segment count that minimises (rounds of units per CTA) x (tiles per unit).
+static SearchPlan make_plan(long long n_rows, int n_query, int n_cta) {
+    SearchPlan pl{};
+    pl.n_qblocks = (n_query + kBM - 1) / kBM;
+    pl.n_tiles = static_cast<int>((n_rows + kSearchBN - 1) / kSearchBN);
+    long long best = -1;
+    for (int s = 1; s <= kMaxSegments && s <= pl.n_tiles; ++s) {
+        const int len = (pl.n_tiles + s - 1) / s;
+        const int segs = (pl.n_tiles + len - 1) / len;
+        const long long rounds = (static_cast<long long>(pl.n_qblocks) * segs + n_cta - 1) / n_cta;
+        const long long cost = rounds * len + rounds;  // + flush overhead per unit
+        if (best < 0 || cost < best) {
+            best = cost;
+            pl.n_seg = segs;
+            pl.seg_tiles = len;
+        }
+    }
+    if (pl.n_tiles == 0) { pl.n_seg = 0; pl.seg_tiles = 1; }
+    pl.n_units = pl.n_qblocks * pl.n_seg;
+    pl.grid = pl.n_units < n_cta ? pl.n_units : n_cta;
+    return pl;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused top-K' epilogue.  Thread <-> accumulator row <-> query.  List slot j of thread t is
+// ls[j * 128 + t] / li[j * 128 + t] (conflict-free across a warp).
+// ---------------------------------------------------------------------------------------
+template <int KCAP>
+struct EpiTopK {
+    struct Params {
+        const float* half_sqnorm;  // (n_rows) 0.5|g|^2, or nullptr for the dot metric
+        long long n_rows;
+        int n_query;
+        uint32_t* thr_enc;         // (n_qblocks * 128) encoded per-query thresholds
+        float* cand_s;             // [n_units][128][KCAP]
+        int* cand_i;               // [n_units][128][KCAP] shard-local row ids
+        int* cand_n;               // [n_units][128]
+    };
+    static constexpr int kSmemBytes = KCAP * 128 * 8;
+
+    float* ls;
+    int* li;
+    int cnt, lpos;
+    float lmin, thr;  // accept  s >= thr
+    bool full;
+
+    __device__ void begin(const Params&, const SchedSearch&, int quarter, int lane, uint8_t* smem) {
+        const int t = quarter * 32 + lane;
+        ls = reinterpret_cast<float*>(smem) + t;
+        li = reinterpret_cast<int*>(smem + KCAP * 128 * 4) + t;
+        cnt = 0; lpos = 0; lmin = 0.f; thr = -INFINITY; full = false;
+    }
+
+    // evict candidate = lowest score, highest index among equal scores.  Static + by-value so
+    // the per-thread state stays in registers (no `this` escaping into local memory).
+    static __device__ __noinline__ float2 find_evict(const float* ls, const int* li) {
+        float mn = ls[0];
+        int mi = li[0], mp = 0;
+#pragma unroll 8
+        for (int j = 1; j < KCAP; ++j) {
+            const float s = ls[j * 128];
+            const int i = li[j * 128];
+            if (s < mn || (s == mn && i > mi)) { mn = s; mi = i; mp = j; }
+        }
+        return make_float2(mn, __int_as_float(mp));
+    }
+    __device__ __forceinline__ void rescan() {
+        const float2 r = find_evict(ls, li);
+        lmin = r.x;
+        lpos = __float_as_int(r.y);
+        thr = next_up(r.x);
+    }
+
+    __device__ __forceinline__ void insert(float s, int idx) {
+        if (!full) {
+            ls[cnt * 128] = s;
+            li[cnt * 128] = idx;
+            if (++cnt == KCAP) { full = true; rescan(); }
+        } else {
+            ls[lpos * 128] = s;
+            li[lpos * 128] = idx;
+            rescan();
+        }
+    }
+
+    __device__ void tile(const Params& p, const SchedSearch& s, uint32_t t_acc, int quarter,
+                         int lane, uint8_t*) {
+        const int row = s.m0 + quarter * 32 + lane;
+        const bool live = row < p.n_query;
+        if (s.first) {
+            cnt = 0;
+            full = false;
+            thr = live ? dec_score(__ldcg(p.thr_enc + row)) : INFINITY;
+        }
+        const long long col_lim = p.n_rows - s.n0;  // columns >= col_lim are padding
+#pragma unroll 1
+        for (int c = 0; c < kSearchBN; c += 32) {
+            uint32_t raw[32];
+            tmem_ld_32x32(t_acc + c, raw);
+            float hb = 0.f;
+            if (p.half_sqnorm && c + lane < col_lim) hb = -__ldg(p.half_sqnorm + s.n0 + c + lane);
+            tmem_ld_wait();
+            float v[32];
+            float mx = -INFINITY;
+            if (p.half_sqnorm) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = __uint_as_float(raw[i]) + __shfl_sync(0xffffffffu, hb, i);
+                    mx = fmaxf(mx, v[i]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = __uint_as_float(raw[i]);
+                    mx = fmaxf(mx, v[i]);
+                }
+            }
+            if (mx >= thr) {  // rare once the threshold has warmed up
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (v[i] >= thr && c + i < col_lim) insert(v[i], s.n0 + c + i);
+                }
+            }
+        }
+        if (s.last) {
+            const long long slot = static_cast<long long>(s.unit) * 128 + quarter * 32 + lane;
+            const int n = live ? cnt : 0;
+            for (int j = 0; j < n; ++j) {
+                p.cand_s[slot * KCAP + j] = ls[j * 128];
+                p.cand_i[slot * KCAP + j] = li[j * 128];
+            }
+            p.cand_n[slot] = n;
+            if (live && full) atomicMax(p.thr_enc + row, enc_score(lmin));
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// fp32 -> bf16 rows (queries), and gallery packing (bf16 rows + 0.5|g|^2 from the fp32 data)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+to_bf16_kernel(const float* __restrict__ in, long long n, __nv_bfloat16* __restrict__ out) {
+    const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4;
+    if (i >= n) return;
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(out + i) = u;
+}
+
+__global__ void __launch_bounds__(256)
+gallery_pack_kernel(const float* __restrict__ g, long long n_rows, int dim,
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ half_sqnorm) {
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    float ss = 0.f;
+    for (int e = lane * 4; e < dim; e += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(g + row * dim + e);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(out + row * dim + e) = u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) half_sqnorm[row] = 0.5f * ss;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 2: merge + exact re-rank.  One CTA per query.
+// key = enc(score) << 32 | (0xFFFFFFFF - idx): descending key = score desc, index asc.
+// ---------------------------------------------------------------------------------------
+struct MergeArgs {
+    const float* cand_s;
+    const int* cand_i;
+    const int* cand_n;
+    int kcap, n_seg, n_qblocks, n_pad;  // n_pad = pow2 >= n_seg * kcap
+    const float* queries;       // (nq, dim) fp32
+    const float* gallery_f32;   // (n_rows, dim) fp32 or nullptr (no re-rank: bf16-pass scores)
+    int dim, metric, k;
+    long long id_offset;
+    double* out_score;          // (nq, k)
+    long long* out_idx;         // (nq, k)
+};
+
+constexpr int kMergeThreads = 256;
+constexpr int kMaxRerank = 64;
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_rerank_kernel(const MergeArgs a) {
+    extern __shared__ unsigned long long keys[];
+    __shared__ double r_score[kMaxRerank];
+    __shared__ long long r_idx[kMaxRerank];
+    __shared__ int n_valid;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int qb = q / kBM, r = q % kBM;
+    if (tid == 0) n_valid = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int e = tid; e < a.n_pad; e += kMergeThreads) {
+        const int seg = e / a.kcap, j = e - seg * a.kcap;
+        unsigned long long key = 0ull;
+        if (seg < a.n_seg) {
+            const long long slot = (static_cast<long long>(seg) * a.n_qblocks + qb) * 128 + r;
+            if (j < a.cand_n[slot]) {
+                const float s = a.cand_s[slot * a.kcap + j];
+                const uint32_t idx = static_cast<uint32_t>(a.cand_i[slot * a.kcap + j]);
+                key = (static_cast<unsigned long long>(enc_score(s)) << 32) | (0xFFFFFFFFu - idx);
+                ++mine;
+            }
+        }
+        keys[e] = key;
+    }
+    if (mine) atomicAdd(&n_valid, mine);
+    __syncthreads();
+    // bitonic sort, descending
+    for (int size = 2; size <= a.n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int e = tid; e < a.n_pad / 2; e += kMergeThreads) {
+                const int lo = 2 * e - (e & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long x = keys[lo], y = keys[hi];
+                if ((x < y) == desc) { keys[lo] = y; keys[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    const int n_r = min(min(n_valid, a.kcap), kMaxRerank);
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int c = warp; c < n_r; c += kMergeThreads / 32) {
+        const unsigned long long key = keys[c];
+        const long long idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+        double score;
+        if (a.gallery_f32) {
+            const float* g = a.gallery_f32 + idx * a.dim;
+            const float* qv = a.queries + static_cast<long long>(q) * a.dim;
+            double acc = 0.0, nn = 0.0;
+            for (int d = lane; d < a.dim; d += 32) {
+                const double gv = static_cast<double>(g[d]);
+                acc = fma(static_cast<double>(qv[d]), gv, acc);
+                nn = fma(gv, gv, nn);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                nn += __shfl_xor_sync(0xffffffffu, nn, o);
+            }
+            score = a.metric == OFX_METRIC_L2 ? acc - 0.5 * nn : acc;
+        } else {
+            score = static_cast<double>(dec_score(static_cast<uint32_t>(key >> 32)));
+        }
+        if (lane == 0) { r_score[c] = score; r_idx[c] = idx; }
+    }
+    __syncthreads();
+    if (tid < a.k) {
+        const long long o = static_cast<long long>(q) * a.k + tid;
+        if (tid >= n_r) { a.out_score[o] = -INFINITY; a.out_idx[o] = -1; }
+    }
+    if (tid < n_r) {
+        const double s = r_score[tid];
+        const long long id = r_idx[tid];
+        int rank = 0;
+        for (int j = 0; j < n_r; ++j) {
+            const double sj = r_score[j];
+            rank += (sj > s) || (sj == s && r_idx[j] < id);
+        }
+        if (rank < a.k) {
+            const long long o = static_cast<long long>(q) * a.k + rank;
+            a.out_score[o] = s;
+            a.out_idx[o] = a.id_offset + id;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Merge of R per-shard lists (after the all-gather): rank by (-score, idx), padding last.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const double* __restrict__ scores, const long long* __restrict__ idx, int n_lists,
+                  int n_query, int k, double* __restrict__ out_score, long long* __restrict__ out_idx) {
+    extern __shared__ unsigned char sm[];
+    const int n = n_lists * k;
+    double* s = reinterpret_cast<double*>(sm);
+    long long* id = reinterpret_cast<long long*>(sm + sizeof(double) * n);
+    const int q = blockIdx.x;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int l = e / k, j = e - l * k;
+        const long long src = (static_cast<long long>(l) * n_query + q) * k + j;
+        s[e] = scores[src];
+        id[e] = idx[src];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const double se = s[e];
+        const long long ie = id[e];
+        const bool pad_e = ie < 0;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const bool pad_j = id[j] < 0;
+            bool better;
+            if (pad_e != pad_j) better = pad_e;  // real entries before padding
+            else if (pad_e) better = j < e;
+            else better = s[j] > se || (s[j] == se && (id[j] < ie || (id[j] == ie && j < e)));
+            rank += better;
+        }
+        if (rank < k) {
+            out_score[static_cast<long long>(q) * k + rank] = pad_e ? -INFINITY : se;
+            out_idx[static_cast<long long>(q) * k + rank] = pad_e ? -1 : ie;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct PackedGallery {
+    size_t rows_bytes, total;
+};
+static PackedGallery gallery_layout(long long n_rows, int dim) {
+    PackedGallery g{};
+    g.rows_bytes = align_up(static_cast<size_t>(n_rows) * dim * 2, 256);
+    g.total = g.rows_bytes + align_up(static_cast<size_t>(n_rows) * 4, 256);
+    return g;
+}
+
+struct SearchWs {
+    size_t q_bf16, thr, cand_n, cand_s, cand_i, total;
+    int kcap;
+    SearchPlan plan;
+};
+static int kcap_for(int k) { return k <= 16 ? 32 : 64; }
+
+static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
+    SearchWs w{};
+    w.kcap = kcap_for(k);
+    w.plan = make_plan(n_rows, n_query, sm_count());
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    const size_t slots = static_cast<size_t>(w.plan.n_units) * 128;
+    w.q_bf16 = take(static_cast<size_t>(n_query) * dim * 2);
+    w.thr = take(static_cast<size_t>(w.plan.n_qblocks) * 128 * 4);
+    w.cand_n = take(slots * 4);
+    w.cand_s = take(slots * w.kcap * 4);
+    w.cand_i = take(slots * w.kcap * 4);
+    w.total = o;
+    return w;
+}
+
+template <int KCAP, int STAGES>
+static int launch_search(const CUtensorMap& tm_q, const CUtensorMap& tm_g, const SearchPlan& pl,
+                         const typename EpiTopK<KCAP>::Params& ep, int dim, cudaStream_t stream) {
+    using Epi = EpiTopK<KCAP>;
+    auto kern = tc_kernel<kSearchBN, STAGES, SchedSearch, Epi>;
+    constexpr int smem = tc_smem_bytes<kSearchBN, STAGES, Epi>();
+    static bool configured = false;
+    if (!configured) {
+        OFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    SchedSearch::Params sp{pl.n_qblocks, pl.n_tiles, pl.seg_tiles, pl.n_units};
+    kern<<<pl.grid, kTcThreads, smem, stream>>>(tm_q, tm_g, sp, ep, dim / kBK);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+}  // namespace ofx
+
+using namespace ofx;
+
+extern "C" {
+
+size_t ofx_gallery_packed_bytes(int64_t n_rows, int32_t dim) {
+    if (n_rows < 0 || dim <= 0) return 0;
+    return gallery_layout(n_rows, dim).total;
+}
+
+int ofx_gallery_pack(const float* gallery, int64_t n_rows, int32_t dim, void* packed, void* stream) {
+    if (n_rows < 0 || n_rows >= (1ll << 31)) return fail(OFX_E_SHAPE, "ofx_gallery_pack: n_rows %lld", (long long)n_rows);
+    if (dim <= 0 || dim % 128) return fail(OFX_E_SHAPE, "ofx_gallery_pack: dim %d must be a multiple of 128", dim);
+    if (n_rows == 0) return OFX_OK;
+    if (!gallery || !packed) return fail(OFX_E_ARG, "ofx_gallery_pack: null argument");
+    if (reinterpret_cast<uintptr_t>(gallery) % 16 || reinterpret_cast<uintptr_t>(packed) % 256)
+        return fail(OFX_E_ARG, "ofx_gallery_pack: misaligned pointer (gallery 16 B, packed 256 B)");
+    OFX_TRY(require_sm100());
+    const PackedGallery L = gallery_layout(n_rows, dim);
+    uint8_t* base = static_cast<uint8_t*>(packed);
+    gallery_pack_kernel<<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        gallery, n_rows, dim, reinterpret_cast<__nv_bfloat16*>(base), reinterpret_cast<float*>(base + L.rows_bytes));
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+size_t ofx_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_query, int32_t k) {
+    if (n_rows < 0 || dim <= 0 || n_query < 0 || k < 1 || k > 48) return 0;
+    return search_ws(n_rows, dim, n_query, k).total;
+}
+
+int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows, int32_t dim,
+                    int64_t id_offset, const float* queries, int32_t n_query, int32_t k, int32_t metric,
+                    double* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+    if (k < 1 || k > 48) return fail(OFX_E_SHAPE, "ofx_topk_search: k %d not in [1,48]", k);
+    if (dim <= 0 || dim % 128) return fail(OFX_E_SHAPE, "ofx_topk_search: dim %d must be a multiple of 128", dim);
+    if (n_rows < 0 || n_rows >= (1ll << 31) - 256) return fail(OFX_E_SHAPE, "ofx_topk_search: n_rows %lld", (long long)n_rows);
+    if (n_query < 0) return fail(OFX_E_SHAPE, "ofx_topk_search: n_query %d", n_query);
+    if (metric != OFX_METRIC_DOT && metric != OFX_METRIC_L2) return fail(OFX_E_ARG, "ofx_topk_search: metric %d", metric);
+    if (n_query == 0) return OFX_OK;
+    if (!queries || !out_score || !out_idx) return fail(OFX_E_ARG, "ofx_topk_search: null argument");
+    if (n_rows > 0 && !packed) return fail(OFX_E_ARG, "ofx_topk_search: packed gallery is null");
+    if (reinterpret_cast<uintptr_t>(queries) % 16 || reinterpret_cast<uintptr_t>(packed) % 256 ||
+        reinterpret_cast<uintptr_t>(workspace) % 256 || reinterpret_cast<uintptr_t>(gallery_f32) % 16)
+        return fail(OFX_E_ARG, "ofx_topk_search: misaligned pointer");
+    OFX_TRY(require_sm100());
+    const SearchWs W = search_ws(n_rows, dim, n_query, k);
+    if (!workspace || workspace_bytes < W.total)
+        return fail(OFX_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, W.total);
+    if (W.plan.n_seg * W.kcap > 8192) return fail(OFX_E_SHAPE, "ofx_topk_search: candidate fan-in too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const uint8_t* pk = static_cast<const uint8_t*>(packed);
+    const PackedGallery L = gallery_layout(n_rows, dim);
+    __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + W.q_bf16);
+    uint32_t* thr = reinterpret_cast<uint32_t*>(ws + W.thr);
+    int* cand_n = reinterpret_cast<int*>(ws + W.cand_n);
+    float* cand_s = reinterpret_cast<float*>(ws + W.cand_s);
+    int* cand_i = reinterpret_cast<int*>(ws + W.cand_i);
+
+    if (n_rows > 0) {
+        const long long nq_el = static_cast<long long>(n_query) * dim;
+        to_bf16_kernel<<<static_cast<unsigned>((nq_el / 4 + 255) / 256), 256, 0, st>>>(queries, nq_el, q_bf16);
+        OFX_LAUNCH_CHECK();
+        OFX_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(W.plan.n_qblocks) * 128 * 4, st));
+        CUtensorMap tm_q, tm_g;
+        OFX_TRY(make_tmap_bf16(&tm_q, q_bf16, static_cast<uint64_t>(n_query), dim, dim, kBM));
+        OFX_TRY(make_tmap_bf16(&tm_g, pk, static_cast<uint64_t>(n_rows), dim, dim, kSearchBN));
+        const float* half = metric == OFX_METRIC_L2 ? reinterpret_cast<const float*>(pk + L.rows_bytes) : nullptr;
+        if (W.kcap == 32) {
+            EpiTopK<32>::Params ep{half, n_rows, n_query, thr, cand_s, cand_i, cand_n};
+            OFX_TRY((launch_search<32, 4>(tm_q, tm_g, W.plan, ep, dim, st)));
+        } else {
+            EpiTopK<64>::Params ep{half, n_rows, n_query, thr, cand_s, cand_i, cand_n};
+            OFX_TRY((launch_search<64, 3>(tm_q, tm_g, W.plan, ep, dim, st)));
+        }
+    }
+    MergeArgs ma{};
+    ma.cand_s = cand_s; ma.cand_i = cand_i; ma.cand_n = cand_n;
+    ma.kcap = W.kcap; ma.n_seg = W.plan.n_seg; ma.n_qblocks = W.plan.n_qblocks;
+    int n_pad = 2;
+    while (n_pad < W.plan.n_seg * W.kcap) n_pad <<= 1;
+    ma.n_pad = n_pad;
+    ma.queries = queries; ma.gallery_f32 = gallery_f32; ma.dim = dim; ma.metric = metric; ma.k = k;
+    ma.id_offset = id_offset; ma.out_score = out_score; ma.out_idx = reinterpret_cast<long long*>(out_idx);
+    const size_t smem = static_cast<size_t>(n_pad) * 8;
+    static bool configured = false;
+    if (!configured) {
+        OFX_CUDA(cudaFuncSetAttribute(merge_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+        configured = true;
+    }
+    merge_rerank_kernel<<<n_query, kMergeThreads, smem, st>>>(ma);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+int ofx_topk_merge(const double* scores, const int64_t* idx, int32_t n_lists, int32_t n_query, int32_t k,
+                   double* out_score, int64_t* out_idx, void* stream) {
+    if (n_lists < 1 || k < 1 || n_query < 0 || static_cast<long long>(n_lists) * k > 2048)
+        return fail(OFX_E_SHAPE, "ofx_topk_merge: n_lists %d, k %d", n_lists, k);
+    if (n_query == 0) return OFX_OK;
+    if (!scores || !idx || !out_score || !out_idx) return fail(OFX_E_ARG, "ofx_topk_merge: null argument");
+    OFX_TRY(require_sm100());
+    const size_t smem = static_cast<size_t>(n_lists) * k * 16;
+    topk_merge_kernel<<<n_query, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        scores, reinterpret_cast<const long long*>(idx), n_lists, n_query, k, out_score,
+        reinterpret_cast<long long*>(out_idx));
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+}

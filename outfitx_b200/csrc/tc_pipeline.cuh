@@ -1,0 +1,168 @@
+// Warp-specialised tcgen05 / TMEM / TMA pipeline shared by the encoder GEMMs and the CIR
+// search kernel (sm_100a only).
+//
+//   D[128 x BN] (fp32, TMEM)  =  A[128 x K] (bf16, K-major)  *  B[BN x K]^T (bf16, K-major)
+//
+// One persistent CTA per SM, 8 warps:
+//   warp 0      TMA producer   (one lane): global -> 128B-swizzled smem ring, mbarrier tx
+//   warp 1      MMA issuer     (one lane): tcgen05.mma kind::f16, M=128, N=BN, K=16 x4 / stage
+//   warp 2      TMEM allocator (2*BN fp32 columns = two accumulator buffers)
+//   warps 4..7  epilogue       (thread t <-> accumulator row t): tcgen05.ld + Epi::tile()
+// Three barrier rings: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+// The tile sequence comes from a Sched object that all roles evaluate identically.
+#pragma once
+#include <cuda.h>
+
+#include "ptx.cuh"
+
+namespace ofx {
+
+constexpr int kBM = 128;       // accumulator rows per CTA tile (UMMA M, cta_group::1)
+constexpr int kBK = 64;        // bf16 elements per smem row = 128 B = one swizzle span
+constexpr int kUmmaK = 16;     // K per tcgen05.mma for 16-bit inputs
+constexpr int kTcThreads = 256;
+constexpr int kEpiWarp0 = 4;   // first epilogue warp (warp % 4 selects the TMEM lane quarter)
+
+template <int BN, int STAGES>
+struct TcCfg {
+    static constexpr int kABytes = kBM * kBK * 2;
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = STAGES;
+    static constexpr int kTmemCols = 2 * BN;  // power of two for BN in {64,128,256}
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    static constexpr int kBarBytes = 256;  // barriers + tmem slot
+};
+
+template <int BN, int STAGES, class Epi>
+constexpr int tc_smem_bytes() {
+    return 1024 /*alignment slack*/ + TcCfg<BN, STAGES>::kRingBytes + TcCfg<BN, STAGES>::kBarBytes +
+           Epi::kSmemBytes;
+}
+
+// Sched concept:
+//   struct Params;  __device__ Sched(const Params&, int cta, int n_cta);
+//   __device__ bool next();          advance to the next tile of this CTA
+//   int m0, n0;                      tile origin (rows of A, rows of B)
+// Epi concept:
+//   struct Params; static constexpr int kSmemBytes;
+//   __device__ void begin(const Params&, const Sched&, int quarter, int lane, uint8_t* smem);
+//   __device__ void tile(const Params&, const Sched&, uint32_t tmem_acc,
+//                        int quarter /*0..3*/, int lane, uint8_t* epi_smem);
+//   (an object per epilogue thread: state such as running top-k thresholds lives in it)
+template <int BN, int STAGES, class Sched, class Epi>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+          const typename Sched::Params sp, const typename Epi::Params ep, const int num_k_blocks) {
+    using Cfg = TcCfg<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte aligned bases
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* s_a = smem;
+    uint8_t* s_b = smem + Cfg::kStages * Cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes);
+    uint64_t* full = bars;                       // [kStages]
+    uint64_t* empty = bars + Cfg::kStages;       // [kStages]
+    uint64_t* tmem_full = bars + 2 * Cfg::kStages;       // [2]
+    uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+    uint8_t* epi_smem = smem + Cfg::kRingBytes + Cfg::kBarBytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            Sched sched(sp, blockIdx.x, gridDim.x);
+            int stage = 0;
+            uint32_t phase = 0;
+            while (sched.next()) {
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+                    tma_load_2d(s_a + stage * Cfg::kABytes, &tm_a, &full[stage], kb * kBK, sched.m0);
+                    tma_load_2d(s_b + stage * Cfg::kBBytes, &tm_b, &full[stage], kb * kBK, sched.n0);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+            Sched sched(sp, blockIdx.x, gridDim.x);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            while (sched.next()) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(s_a + stage * Cfg::kABytes);
+                    const uint32_t b_addr = smem_u32(s_b + stage * Cfg::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
+                                  umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);  // frees the smem slot when the MMAs retire
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ------------------------------------------------------------ epilogue
+        const int quarter = warp & 3;
+        Sched sched(sp, blockIdx.x, gridDim.x);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        Epi epi;
+        epi.begin(ep, sched, quarter, lane, epi_smem);
+        while (sched.next()) {
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+            epi.tile(ep, sched, t_acc, quarter, lane, epi_smem);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+}  // namespace ofx

@@ -1,0 +1,123 @@
+"""GPU parity of the CIR search (ofx_topk_search / ofx_topk_merge) against the fp64 oracle
+(oracle/search_oracle.c, itself pinned to the reference idiom topk(cdist) in tests/golden).
+
+Bar (BASELINE.json north_star): exact search -> indices bit-exact vs the fp64 (-score, idx)
+oracle; bf16 pass alone -> recall@10 >= 0.999.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from outfitx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def _search(q, gal, k, metric="l2", exact=True, id_offset=0):
+    from outfitx_b200.search import Gallery, local_search
+    G = Gallery.build(_t(gal), id_offset=id_offset)
+    idx, score = local_search(_t(q), G, k, metric, exact)
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), score.cpu().numpy()
+
+
+def test_reference_pool_golden(golden_dir):
+    """The trainer's own setting: a 3000-item category pool, k = 50 would exceed MAX_K -> k = 48."""
+    g = np.load(os.path.join(golden_dir, "search_pool3000.npz"))
+    pool = synth.make_items(3000, 512, seed=int(g["pool_seed"]))
+    q = synth.make_queries(64, 1024, seed=int(g["query_seed"])) * np.float32(0.05)
+    idx, score = _search(q, pool, 48)
+    want_i, want_s = R.search(q, pool, k=48)
+    assert np.array_equal(idx, want_i)
+    np.testing.assert_allclose(score, want_s, rtol=0, atol=1e-12)
+    # top-10 equal to the reference's fp32 topk(cdist) output itself
+    assert np.array_equal(idx[:, :10], g["indices"][:, :10])
+
+
+@pytest.mark.parametrize("n,nq,k,metric", [
+    (20000, 300, 10, "l2"), (20000, 300, 10, "dot"), (5000, 7, 1, "l2"), (100, 130, 16, "dot"),
+    (257, 5, 10, "l2"), (70001, 129, 32, "l2")])
+def test_exact_indices_with_duplicates(n, nq, k, metric):
+    gal = synth.make_items(n, 512, seed=n, dup=min(1000, n // 4))
+    if metric == "l2":  # break the |g|^2 == 2 degeneracy so that the bias term matters
+        gal = gal * (1.0 + 0.2 * synth.make_queries(n, 1, seed=n + 1)).astype(np.float32)
+    q = synth.make_queries(nq, 1024, seed=n + 2)
+    idx, score = _search(q, gal, k, metric, id_offset=12345)
+    want_i, want_s = R.search(q, gal, k=k, metric=metric, id_offset=12345)
+    assert np.array_equal(idx, want_i)
+    np.testing.assert_allclose(score, want_s, rtol=1e-13, atol=1e-11)
+
+
+def test_small_and_empty_galleries():
+    q = synth.make_queries(4, 1024, seed=1)
+    gal = synth.make_items(6, 512, seed=2)
+    idx, score = _search(q, gal, 10)
+    want_i, want_s = R.search(q, gal, k=10)
+    assert np.array_equal(idx, want_i)          # 6 real entries then -1 padding
+    assert np.all(idx[:, 6:] == -1) and np.all(np.isneginf(score[:, 6:]))
+    idx, score = _search(q, gal[:0], 3)
+    assert np.all(idx == -1) and np.all(np.isneginf(score))
+    idx, _ = _search(q[:0], gal, 3)
+    assert idx.shape == (0, 3)
+
+
+def test_bf16_pass_recall():
+    n, nq = 200_000, 512
+    gal = synth.make_items(n, 512, seed=77)
+    q = synth.make_queries(nq, 1024, seed=78)
+    idx, _ = _search(q, gal, 10, "l2", exact=False)
+    want_i, _ = R.search(q, gal, k=10)
+    hits = sum(len(set(a) & set(b)) for a, b in zip(idx, want_i))
+    assert hits / want_i.size >= 0.999
+    idx_exact, _ = _search(q, gal, 10, "l2", exact=True)
+    assert np.array_equal(idx_exact, want_i)
+
+
+def test_sharded_search_equals_single(golden_dir):
+    """Gallery sharding emulated on one GPU: per-shard local search with global ids, then the
+    merge kernel -- must equal the unsharded search and the oracle, for every world size."""
+    from outfitx_b200.search import Gallery, local_search, merge_lists, shard_rows
+    n, nq, k = 30_001, 200, 10
+    gal = synth.make_items(n, 512, seed=5, dup=1000)
+    q = synth.make_queries(nq, 1024, seed=6)
+    want_i, want_s = R.search(q, gal, k=k)
+    full = _t(gal)
+    for world in (1, 2, 4, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_rows(n, r, world)
+            G = Gallery.build(full[lo:hi], id_offset=lo)
+            parts.append(local_search(_t(q), G, k))
+        idx = torch.stack([p[0] for p in parts])
+        score = torch.stack([p[1] for p in parts])
+        mi, ms = merge_lists(idx, score, k)
+        assert np.array_equal(mi.cpu().numpy(), want_i)
+        np.testing.assert_allclose(ms.cpu().numpy(), want_s, rtol=1e-13, atol=1e-11)
+
+
+def test_queries_from_the_encoder_find_planted_items():
+    """End to end CIR: encoder-produced queries, gallery with each query's own embedding planted
+    at a known row -> rank 0 must be the planted row (distance 0)."""
+    import outfitx_b200 as o
+    sd = synth.make_state_dict(1024, 1024, seed=0)
+    m = o.OutfitX(o.OutfitXConfig(item_encoder=o.ItemEncoderConfig(type="clip")), precision="bf16")
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.to(DEV)
+    B = 64
+    emb, mask, _ = synth.make_outfits(B, "concat", seed=91)
+    text = synth.make_text_prefix(B, 512, seed=92)
+    qv = m.cir_embed(_t(emb), _t(mask), _t(text))
+    gal = _t(synth.make_items(10_000, 512, seed=93))
+    rows = torch.arange(B, device=DEV) * 150 + 7
+    gal[rows] = qv
+    from outfitx_b200.search import Gallery, cir_search
+    idx, score = cir_search(qv, Gallery.build(gal), k=10, metric="l2")
+    assert torch.equal(idx[:, 0], rows)
