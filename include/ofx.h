@@ -95,6 +95,8 @@ enum {
 
 OFX_API int ofx_version(void);
 OFX_API const char* ofx_last_error(void);
+/* number of CUDA kernels this library has launched in this process (all threads) */
+OFX_API int64_t ofx_launch_count(void);
 /* 0 when cuda device `device` has compute capability 10.x, else OFX_E_ARCH */
 OFX_API int ofx_device_ok(int device);
 

@@ -50,6 +50,7 @@ class ForwardArgs(C.Structure):
 _SIGNATURES = {
     "ofx_version": (C.c_int, []),
     "ofx_last_error": (C.c_char_p, []),
+    "ofx_launch_count": (C.c_int64, []),
     "ofx_device_ok": (C.c_int, [C.c_int]),
     "ofx_packed_weights_bytes": (C.c_size_t, [C.POINTER(Shape)]),
     "ofx_pack_weights": (C.c_int, [C.POINTER(Shape), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),

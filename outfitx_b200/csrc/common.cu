@@ -1,7 +1,10 @@
 #include "common.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
 
 namespace ofx {
 
@@ -23,6 +26,10 @@ int fail(int code, const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 static int g_sm_count = 0;
 
@@ -46,6 +53,18 @@ int sm_count() {
             g_sm_count = 148;
     }
     return g_sm_count;
+}
+
+int cluster_size() {
+    static int cl = 0;
+    if (cl == 0) {
+        cl = 2;
+        if (const char* e = getenv("OFX_CLUSTER")) {
+            const int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4) cl = v;
+        }
+    }
+    return cl;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -92,6 +111,8 @@ extern "C" {
 int ofx_version(void) { return OFX_VERSION; }
 
 const char* ofx_last_error(void) { return ofx::last_error(); }
+
+int64_t ofx_launch_count(void) { return ofx::launches(); }
 
 int ofx_device_ok(int device) {
     int major = 0, n = 0;

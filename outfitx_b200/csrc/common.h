@@ -30,7 +30,15 @@ const char* last_error();
         if (rc__ != OFX_OK) return rc__; \
     } while (0)
 
-#define OFX_LAUNCH_CHECK() OFX_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this: error check + launch counter
+// (ofx_launch_count, read by bench.py for its gpu_launches claim)
+void count_launch();
+long long launches();
+#define OFX_LAUNCH_CHECK()            \
+    do {                              \
+        ::ofx::count_launch();        \
+        OFX_CUDA(cudaGetLastError()); \
+    } while (0)
 
 // Requires a device of compute capability 10.x (the kernels are sm_100a-only).
 int require_sm100();
@@ -40,6 +48,9 @@ int sm_count();
 // elements (128 B) with the 128-byte swizzle the UMMA descriptors expect; OOB reads give zeros.
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                    uint32_t box_rows);
+
+// cluster size used by the tcgen05 kernels (1, 2 or 4): OFX_CLUSTER overrides the default of 2
+int cluster_size();
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

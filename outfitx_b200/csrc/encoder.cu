@@ -92,7 +92,7 @@ static int pack_all(const WLayout& L, const float* const* p, uint8_t* dst, cudaS
 
 // workspace carve-up (all 256-byte aligned)
 struct WsLayout {
-    size_t off, n_tok, x, h, big, q0, a0, u0, total;
+    size_t off, n_tok, owner, x, h, big, q0, a0, u0, total;
     int t_max, big_ld;
 };
 static WsLayout make_ws(const ofx_shape* s, int batch) {
@@ -106,6 +106,7 @@ static WsLayout make_ws(const ofx_shape* s, int batch) {
     const size_t t = static_cast<size_t>(W.t_max);
     W.off = take((static_cast<size_t>(batch) + 1) * 4);
     W.n_tok = take(4);
+    W.owner = take(t * 4);
     W.x = take(t * dm * 4);
     W.h = take(t * dm * esz);
     W.big = take(t * W.big_ld * esz);
@@ -128,6 +129,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
     const int B = a->batch, dm = L.dm, fp = L.fp, hd = dm / s->n_head;
     int* off = reinterpret_cast<int*>(ws + W.off);
     int* n_tok = reinterpret_cast<int*>(ws + W.n_tok);
+    int* owner = reinterpret_cast<int*>(ws + W.owner);
     float* x = reinterpret_cast<float*>(ws + W.x);
     T* h = reinterpret_cast<T*>(ws + W.h);
     T* big = reinterpret_cast<T*>(ws + W.big);
@@ -148,6 +150,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
     as.target_img = reinterpret_cast<const float*>(wts + L.g_timg);
     as.text = a->text;
     as.ln_w = lf(0, L.ln1w); as.ln_b = lf(0, L.ln1b);
+    as.owner = owner;
     OFX_TRY(assemble<T>(as, dm, x, h, st));
 
     for (int l = 0; l < L.nl; ++l) {
@@ -155,6 +158,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
         if (l > 0) OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln1w), lf(l, L.ln1b), h, st));
         AttnArgs at{};
         at.batch = B; at.n_head = s->n_head; at.off = off;
+        at.max_rows = W.t_max; at.n_tok = n_tok; at.owner = owner;
         if (!last) {
             // dense layer over every valid token
             GemmArgs g{h, dm, lw(l, L.w_qkv), dm, W.t_max, n_tok, 3 * dm, dm, lf(l, L.b_qkv), 0, nullptr, 0, big, 3 * dm, 0};

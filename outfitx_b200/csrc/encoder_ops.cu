@@ -241,6 +241,7 @@ assemble_kernel(AssembleArgs a, float* __restrict__ x, T* __restrict__ h) {
         int rank = 0;
         for (int j = 0; j < s - 1; ++j) rank += m[j] == 0;
         row = a.batch + a.off[b] + rank;
+        if (lane == 0) a.owner[row] = b;
         const long long item = static_cast<long long>(b) * a.max_items + (s - 1);
         if (a.emb) {
 #pragma unroll
@@ -330,95 +331,128 @@ template int cast_rows<float>(const float*, long long, float*, cudaStream_t);
 template int cast_rows<__nv_bfloat16>(const float*, long long, __nv_bfloat16*, cudaStream_t);
 
 // ------------------------------------------------------------------ attention
-// One warp per (outfit, head).  S = 1 + n_valid <= 17 tokens: K and V head slices are staged
-// in shared memory as fp32; lane i owns query i (scores, softmax and the output row live in
-// its registers); softmax over the S keys only -- dropped pads are exactly the -inf keys of
-// the reference's float mask.  row0_only: the pruned last layer (query = prefix token only).
-template <int HD> struct AttnCfg { static constexpr int kWarps = HD > 64 ? 2 : 4; };
-
+// Four consecutive lanes serve one (token row, head): lane `sub` owns dims {32p + 8 sub .. +8}
+// of the head for every 32-dim piece p, so each warp-wide 16-byte load covers contiguous 64-byte
+// runs (8 heads x 4 lanes = 512 contiguous bytes of one token row at head_dim 32) -- fully
+// coalesced q / K / V loads and output stores, no shared memory.  Partial q.k sums are combined
+// with two xor-shuffles; the S <= 17 scores, the softmax and the output slice stay in registers.
+// Softmax runs over the outfit's S = 1 + n valid tokens only: the dropped pads are exactly the
+// -inf keys of the reference's float key-padding mask.
+// row0_only: the pruned last layer (queries = the B prefix tokens, from a separate buffer).
 template <int HD, class T>
-__global__ void __launch_bounds__(32 * AttnCfg<HD>::kWarps)
+__global__ void __launch_bounds__(256)
 attention_kernel(AttnArgs a) {
     constexpr int kMaxS = 17;
-    constexpr int kWarps = AttnCfg<HD>::kWarps;
-    __shared__ float s_k[kWarps][kMaxS][HD + 1];
-    __shared__ float s_v[kWarps][kMaxS][HD + 1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gw = static_cast<long long>(blockIdx.x) * kWarps + warp;
-    const int b = static_cast<int>(gw / a.n_head), head = static_cast<int>(gw % a.n_head);
-    if (b >= a.batch) return;
+    constexpr int NP = HD / 32;  // 8-dim pieces per lane
+    const int n_rows = a.row0_only ? a.batch : min(*a.n_tok, a.max_rows);
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 6);
+    const int head = (threadIdx.x >> 2) & 15;
+    const int sub = threadIdx.x & 3;
+    if (row >= n_rows) return;  // whole 64-thread groups leave together (shuffles stay inside 4 lanes)
+    const int b = row < a.batch ? row : a.owner[row];
     const int base = a.batch + a.off[b];
     const int S = 1 + (a.off[b + 1] - a.off[b]);
-    const T* kp = static_cast<const T*>(a.k);
-    const T* vp = static_cast<const T*>(a.v);
-    const T* qp = static_cast<const T*>(a.q);
-    T* op = static_cast<T*>(a.out);
-    // stage K, V: each lane moves 8-element (16 B bf16) pieces of the head slices
-    constexpr int kPieces = HD / 8;
-    for (int c = lane; c < S * kPieces; c += 32) {
-        const int j = c / kPieces, d = (c % kPieces) * 8;
-        const long long r = j == 0 ? b : base + j - 1;
-        float t[8];
-        load8(kp + r * a.ldk + head * HD + d, t);
+    const int col = head * HD + sub * 8;
+    const T* kp = static_cast<const T*>(a.k) + col;
+    const T* vp = static_cast<const T*>(a.v) + col;
+    const T* qp = static_cast<const T*>(a.q) + static_cast<long long>(row) * a.ldq + col;
+    T* op = static_cast<T*>(a.out) + static_cast<long long>(row) * a.ldo + col;
+
+    float q[NP][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s_k[warp][j][d + i] = t[i];
-        load8(vp + r * a.ldv + head * HD + d, t);
+    for (int p = 0; p < NP; ++p) load8(qp + 32 * p, q[p]);
+    // Keys are taken four at a time: the four row loads of a group are issued back to back
+    // (rows past S are clamped to key 0 -- a valid, cached address -- and masked afterwards), so
+    // every thread keeps several independent 16-byte loads in flight instead of one.
+    constexpr int kGroups = 5;  // 5 x 4 >= 17
+    float sc[kGroups * 4];
+    const float scale = rsqrtf(static_cast<float>(HD));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s_v[warp][j][d + i] = t[i];
-    }
-    __syncwarp();
-    const int nq = a.row0_only ? 1 : S;
-    if (lane >= nq) return;
-    const long long qr = lane == 0 ? b : base + lane - 1;
-    float sc[kMaxS];
+    for (int g = 0; g < kGroups; ++g) {
 #pragma unroll
-    for (int j = 0; j < kMaxS; ++j) sc[j] = 0.f;
-    // scores: q is streamed from global in chunks of 8 (own row, contiguous)
-    for (int d0 = 0; d0 < HD; d0 += 8) {
-        float q[8];
-        load8(qp + qr * a.ldq + head * HD + d0, q);
+        for (int u = 0; u < 4; ++u) sc[4 * g + u] = -INFINITY;
+        if (4 * g < S) {
+            float t[4][NP][8];
 #pragma unroll
-        for (int j = 0; j < kMaxS; ++j) {
-            if (j < S) {
+            for (int u = 0; u < 4; ++u) {
+                const int j = 4 * g + u;
+                const long long r = (j == 0 || j >= S) ? b : base + j - 1;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sc[j] = fmaf(q[i], s_k[warp][j][d0 + i], sc[j]);
+                for (int p = 0; p < NP; ++p) load8(kp + r * a.ldk + 32 * p, t[u][p]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float acc = 0.f;
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc = fmaf(q[p][e], t[u][p][e], acc);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (4 * g + u < S) sc[4 * g + u] = acc * scale;
             }
         }
     }
-    const float scale = rsqrtf(static_cast<float>(HD));
-    float mx = -INFINITY;
+    float mx = sc[0];
 #pragma unroll
-    for (int j = 0; j < kMaxS; ++j) if (j < S) { sc[j] *= scale; mx = fmaxf(mx, sc[j]); }
+    for (int j = 1; j < kGroups * 4; ++j) mx = fmaxf(mx, sc[j]);
     float den = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxS; ++j) if (j < S) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
-    const float inv = 1.f / den;
-    const long long orow = a.row0_only ? b : qr;
-    for (int d0 = 0; d0 < HD; d0 += 8) {
-        float o[8];
+    for (int g = 0; g < kGroups; ++g) {
+        if (4 * g < S) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = 0.f;
-#pragma unroll
-        for (int j = 0; j < kMaxS; ++j) {
-            if (j < S) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = fmaf(sc[j], s_v[warp][j][d0 + i], o[i]);
+            for (int u = 0; u < 4; ++u) {
+                const float e = sizeof(T) == 4 ? expf(sc[4 * g + u] - mx) : __expf(sc[4 * g + u] - mx);
+                sc[4 * g + u] = e;  // exp(-inf) = 0 for the masked tail of the group
+                den += e;
             }
         }
+    }
+    const float inv = 1.f / den;
+    float o[NP][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] *= inv;
-        store8(op + orow * a.ldo + head * HD + d0, o);
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[p][e] = 0.f;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        if (4 * g < S) {
+            float t[4][NP][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = 4 * g + u;
+                const long long r = (j == 0 || j >= S) ? b : base + j - 1;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) load8(vp + r * a.ldv + 32 * p, t[u][p]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float pj = sc[4 * g + u];
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[p][e] = fmaf(pj, t[u][p][e], o[p][e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[p][e] *= inv;
+        store8(op + 32 * p, o[p]);
     }
 }
 
 template <class T>
 int attention(const AttnArgs& a, int head_dim, cudaStream_t stream) {
     if (a.batch <= 0) return OFX_OK;
-    const long long warps = static_cast<long long>(a.batch) * a.n_head;
+    if (a.n_head != 16) return fail(OFX_E_SHAPE, "attention: n_head %d != 16", a.n_head);
+    const int rows = a.row0_only ? a.batch : a.max_rows;
+    const unsigned grid = static_cast<unsigned>((rows + 3) / 4);
     switch (head_dim) {
-        case 32: attention_kernel<32, T><<<static_cast<unsigned>((warps + 3) / 4), 128, 0, stream>>>(a); break;
-        case 64: attention_kernel<64, T><<<static_cast<unsigned>((warps + 3) / 4), 128, 0, stream>>>(a); break;
-        case 96: attention_kernel<96, T><<<static_cast<unsigned>((warps + 1) / 2), 64, 0, stream>>>(a); break;
+        case 32: attention_kernel<32, T><<<grid, 256, 0, stream>>>(a); break;
+        case 64: attention_kernel<64, T><<<grid, 256, 0, stream>>>(a); break;
+        case 96: attention_kernel<96, T><<<grid, 256, 0, stream>>>(a); break;
         default: return fail(OFX_E_SHAPE, "head_dim %d not in {32,64,96}", head_dim);
     }
     OFX_LAUNCH_CHECK();

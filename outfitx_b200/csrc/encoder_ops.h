@@ -16,10 +16,14 @@ struct AssembleArgs {
     const float* text;          // (B, Dm/2)
     const float* ln_w;          // LayerNorm 1 of layer 0 (fused here)
     const float* ln_b;
+    int* owner;                 // out: (B + total items) token row -> outfit (item rows only)
 };
 
 struct AttnArgs {
     int batch, n_head, row0_only;
+    int max_rows;          // host upper bound of token rows
+    const int* n_tok;      // device token-row count
+    const int* owner;      // token row -> outfit (rows >= batch)
     const int* off;
     const void* q; long long ldq;   // element pitches
     const void* k; long long ldk;

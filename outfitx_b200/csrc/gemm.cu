@@ -12,10 +12,13 @@ namespace ofx {
 // mish(x) = x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)   (SURVEY.md H4);
 // torch's softplus threshold (x > 20 -> x) is kept.
 __device__ __forceinline__ float mish_fast(float x) {
-    float w = __expf(fminf(x, 20.f));
-    float n = w * (w + 2.f);
-    float y = x * __fdividef(n, n + 2.f);
-    return x > 20.f ? x : y;
+    // n / (n + 2) with n = w (w + 2), w = e^x: two MUFU ops (ex2, rcp).  For x >= 20 the ratio
+    // rounds to 1 (torch switches softplus to the identity there); the clamp keeps w^2 finite.
+    float w, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(fminf(x, 40.f) * 1.4426950408889634f));
+    const float n = fmaf(w, w, w + w);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.f));
+    return x * n * r;
 }
 __device__ __forceinline__ float mish_precise(float x) {
     float w = expf(fminf(x, 20.f));
@@ -33,28 +36,42 @@ struct SchedGemm {
         const int* m_dev;  // optional device-side row count (token count after compaction)
         int n_tiles;       // N / BN
         int bn;
+        int cl;            // cluster size: CL consecutive M tiles share one B (weight) tile
     };
     int m0, n0, m_actual;
-    int tile, step, total, n_tiles, bn;
+    int tile, step, total, n_tiles, bn, cl, rank;
     __device__ SchedGemm(const Params& p, int cta, int n_cta) {
         m_actual = p.m_dev ? min(*p.m_dev, p.m) : p.m;
         n_tiles = p.n_tiles;
         bn = p.bn;
-        total = ((m_actual + kBM - 1) / kBM) * n_tiles;
-        tile = cta - n_cta;
-        step = n_cta;
+        cl = p.cl;
+        rank = cta % cl;
+        const int m_groups = ((m_actual + kBM - 1) / kBM + cl - 1) / cl;
+        total = m_groups * n_tiles;
+        step = n_cta / cl;
+        tile = cta / cl - step;
         m0 = n0 = 0;
     }
     __device__ bool next() {
         tile += step;
         if (tile >= total) return false;
-        // n fastest: CTAs that run together share the same rows of A in L2
-        m0 = (tile / n_tiles) * kBM;
+        // n fastest: clusters that run together share the same rows of A in L2.  A CTA whose
+        // M tile lies beyond m_actual still runs the tile (TMA zero-fills, nothing is stored).
+        m0 = ((tile / n_tiles) * cl + rank) * kBM;
         n0 = (tile % n_tiles) * bn;
         return true;
     }
 };
 
+// Epilogue of the linear layers.  8 warps: warp e serves accumulator rows 32*(e&3)..+31 and the
+// column half (e>>2).  Per 32-column slab:
+//   phase A  thread <-> row: tcgen05.ld gives each thread 32 consecutive fp32 columns of its row;
+//            they go to a per-warp 32 x 128 B staging tile in shared memory (16-byte chunks
+//            XOR-swizzled by row so both phases are bank-conflict free);
+//   phase B  lane <-> (row % 4, 16-byte chunk): the warp re-reads the tile four rows at a time and
+//            applies bias / mish / fp32 residual and stores -- every global access of the warp
+//            is now 4 full 128-byte (fp32) or 64-byte (bf16) row segments instead of 32 scattered
+//            16-byte pieces.
 template <int BN>
 struct EpiLinear {
     struct Params {
@@ -66,91 +83,128 @@ struct EpiLinear {
         int act_mish;
         int out_f32;
     };
-    static constexpr int kSmemBytes = 0;
+    static constexpr int kWarps = 8;
+    static constexpr int kSmemBytes = kWarps * 32 * 128;
     __device__ void begin(const Params&, const SchedGemm&, int, int, uint8_t*) {}
-    __device__ void tile(const Params& p, const SchedGemm& s, uint32_t t_acc, int quarter,
-                                int lane, uint8_t*) {
-        const int row = s.m0 + quarter * 32 + lane;
-        const bool live = row < s.m_actual;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+    __device__ void tile(const Params& p, const SchedGemm& s, uint32_t t_acc, int ewarp, int lane,
+                         uint8_t* epi_smem) {
+        const int quarter = ewarp & 3, half = ewarp >> 2;
+        uint8_t* stage = epi_smem + ewarp * (32 * 128);
+        const int sub_row = lane >> 3, chunk = lane & 7;
+        const int row0 = s.m0 + quarter * 32;
+        const int rows_valid = s.m_actual - row0 - sub_row;  // row 4 i + sub_row is live iff 4 i < rows_valid
+        const int col0 = s.n0 + half * (BN / 2) + chunk * 4;
+        const long long first = static_cast<long long>(row0 + sub_row);
+        const float* resp = p.residual ? p.residual + first * p.ldr + col0 : nullptr;
+        float* outf = static_cast<float*>(p.out) + first * p.ldo + col0;
+        __nv_bfloat16* outh = static_cast<__nv_bfloat16*>(p.out) + first * p.ldo + col0;
+        const long long ldr4 = 4 * p.ldr, ldo4 = 4 * p.ldo;
+        constexpr int kSlabs = BN / 2 / 32;
+        // the fp32 residual of a slab is fetched one slab ahead (before any store of this slab,
+        // which may alias it), so its HBM latency hides behind the TMEM read and the staging
+        float4 res[8];
+        if (resp) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                res[i] = 4 * i < rows_valid ? *reinterpret_cast<const float4*>(resp + i * ldr4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int sl = 0; sl < kSlabs; ++sl) {
+            const int c = half * (BN / 2) + sl * 32;
             uint32_t raw[32];
             tmem_ld_32x32(t_acc + c, raw);
-            tmem_ld_wait();
-            if (!live) continue;
-            const int col = s.n0 + c;
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-            if (p.bias) {
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 b = __ldg(b4 + i);
-                    v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-                }
-            }
-            if (p.act_mish) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = mish_fast(v[i]);
-            }
-            if (p.residual) {
-                const float4* r4 =
-                    reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + col);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 r = r4[i];
-                    v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-                }
-            }
-            if (p.out_f32) {
-                float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) +
-                                                       static_cast<long long>(row) * p.ldo + col);
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + sl * 32));
+            float4 nxt[8];
+            if (resp && sl + 1 < kSlabs) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
-                uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) +
-                                                     static_cast<long long>(row) * p.ldo + col);
+                    nxt[i] = 4 * i < rows_valid
+                                 ? *reinterpret_cast<const float4*>(resp + (sl + 1) * 32 + i * ldr4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tmem_ld_wait();
+            __syncwarp();  // previous slab's phase B has finished reading the staging tile
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-                    __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-                    __nv_bfloat162 c2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-                    __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&a);
-                    u.y = *reinterpret_cast<uint32_t*>(&b);
-                    u.z = *reinterpret_cast<uint32_t*>(&c2);
-                    u.w = *reinterpret_cast<uint32_t*>(&d);
-                    o4[i] = u;
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<uint4*>(stage + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                    make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + sub_row;
+                float4 v = *reinterpret_cast<const float4*>(stage + r * 128 + ((chunk ^ (r & 7)) << 4));
+                if (4 * i < rows_valid) {
+                    v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                    if (p.act_mish) { v.x = mish_fast(v.x); v.y = mish_fast(v.y); v.z = mish_fast(v.z); v.w = mish_fast(v.w); }
+                    if (resp) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                    if (p.out_f32) {
+                        *reinterpret_cast<float4*>(outf + sl * 32 + i * ldo4) = v;
+                    } else {
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                        uint2 u;
+                        u.x = *reinterpret_cast<uint32_t*>(&lo);
+                        u.y = *reinterpret_cast<uint32_t*>(&hi);
+                        *reinterpret_cast<uint2*>(outh + sl * 32 + i * ldo4) = u;
+                    }
                 }
+            }
+            if (resp && sl + 1 < kSlabs) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) res[i] = nxt[i];
             }
         }
     }
 };
 
-template <int BN>
+template <int BN, int CL>
 static int launch_tc(const GemmArgs& g, cudaStream_t stream) {
     using Epi = EpiLinear<BN>;
     CUtensorMap tm_a, tm_b;
     OFX_TRY(make_tmap_bf16(&tm_a, g.a, static_cast<uint64_t>(g.m), g.k, g.lda, kBM));
-    OFX_TRY(make_tmap_bf16(&tm_b, g.w, static_cast<uint64_t>(g.n), g.k, g.ldw, BN));
-    SchedGemm::Params sp{g.m, g.m_dev, g.n / BN, BN};
+    OFX_TRY(make_tmap_bf16(&tm_b, g.w, static_cast<uint64_t>(g.n), g.k, g.ldw, BN / CL));
+    SchedGemm::Params sp{g.m, g.m_dev, g.n / BN, BN, CL};
     typename Epi::Params ep{g.bias, g.residual, g.ldr, g.out, g.ldo, g.act_mish, g.out_f32};
-    constexpr int kStages = BN >= 256 ? 4 : 6;
-    auto kern = tc_kernel<BN, kStages, SchedGemm, Epi>;
+    constexpr int kStages = BN >= 256 ? 4 : 5;
+    auto kern = tc_kernel<BN, kStages, CL, SchedGemm, Epi>;
     constexpr int smem = tc_smem_bytes<BN, kStages, Epi>();
     static bool configured = false;  // per instantiation
     if (!configured) {
         OFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    const int tiles = ((g.m + kBM - 1) / kBM) * (g.n / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, kTcThreads, smem, stream>>>(tm_a, tm_b, sp, ep, g.k / kBK);
-    OFX_LAUNCH_CHECK();
+    const int m_groups = ((g.m + kBM - 1) / kBM + CL - 1) / CL;
+    const int tiles = m_groups * (g.n / BN);
+    const int max_clusters = sm_count() / CL;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CL);
+    cfg.blockDim = dim3(tc_threads<Epi>());
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    count_launch();
+    OFX_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, sp, ep, g.k / kBK));
     return OFX_OK;
+}
+
+template <int BN>
+static int launch_tc_cl(const GemmArgs& g, cudaStream_t stream) {
+    const long long m_tiles = (g.m + kBM - 1) / kBM;
+    int cl = cluster_size();
+    while (cl > 1 && m_tiles < cl) cl >>= 1;  // tiny M: nothing to share
+    switch (cl) {
+        case 4: return launch_tc<BN, 4>(g, stream);
+        case 2: return launch_tc<BN, 2>(g, stream);
+        default: return launch_tc<BN, 1>(g, stream);
+    }
 }
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
@@ -165,8 +219,8 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     // BN = 256 halves the A re-reads; use 128 when 256 does not divide N or the grid would
     // leave most SMs idle.
     const long long tiles256 = static_cast<long long>((g.m + kBM - 1) / kBM) * (g.n / 256);
-    if (g.n % 256 == 0 && tiles256 >= sm_count()) return launch_tc<256>(g, stream);
-    return launch_tc<128>(g, stream);
+    if (g.n % 256 == 0 && tiles256 >= sm_count()) return launch_tc_cl<256>(g, stream);
+    return launch_tc_cl<128>(g, stream);
 }
 
 // -------------------------------------------------------------------------------------

@@ -13,6 +13,8 @@
 //   score with one compare.
 // Pass 2: per query, merge the units' lists by (score desc, index asc), re-score the K' best
 //   in fp64 from the fp32 queries / gallery, rank by (-score, index), emit the top k.
+#include <stdlib.h>
+
 #include "common.h"
 #include "tc_pipeline.cuh"
 
@@ -45,52 +47,74 @@ __device__ __forceinline__ float next_up(float x) {
 // ---------------------------------------------------------------------------------------
 struct SchedSearch {
     struct Params {
-        int n_qblocks, n_tiles, seg_tiles, n_units;
+        int n_qgroups, n_tiles, seg_tiles, n_units, sub_tiles, cl;
     };
-    int m0, n0, unit, cur, tile_hi, step;
+    int m0, n0, unit, step, rank;
+    int seg_lo, seg_len, it, qg;
     bool first, last;
     Params p;
+    // With clusters (cl > 1) a unit belongs to a cluster: its cl CTAs take cl consecutive query
+    // blocks (query group qg) and walk the same gallery tiles in the same order.
     __device__ SchedSearch(const Params& pp, int cta, int n_cta) : p(pp) {
-        unit = cta - n_cta;
-        step = n_cta;
-        cur = 0;
-        tile_hi = 0;
+        rank = cta % pp.cl;
+        step = n_cta / pp.cl;
+        unit = cta / pp.cl - step;
+        it = 0;
+        seg_lo = seg_len = qg = 0;
         m0 = n0 = 0;
         first = last = false;
     }
+    // A unit's segment is swept as consecutive L2-sized sub-blocks of p.sub_tiles tiles.  Inside a
+    // sub-block every query block starts at a different tile and wraps around, so the CTAs that
+    // share the sub-block are spread over it instead of all missing on the same lines at once
+    // (L2 merges only a few concurrent misses per line); whoever touches a tile first pulls it
+    // from HBM, everyone else hits it in L2 whatever their relative pace.
     __device__ bool next() {
-        if (cur + 1 < tile_hi) {
-            ++cur;
+        if (it + 1 < seg_len) {
+            ++it;
             first = false;
         } else {
             unit += step;
             if (unit >= p.n_units) return false;
-            const int seg = unit / p.n_qblocks;
-            m0 = (unit - seg * p.n_qblocks) * kBM;
-            cur = seg * p.seg_tiles;
-            tile_hi = min(p.n_tiles, cur + p.seg_tiles);
+            const int seg = unit / p.n_qgroups;
+            qg = unit - seg * p.n_qgroups;
+            m0 = (qg * p.cl + rank) * kBM;
+            seg_lo = seg * p.seg_tiles;
+            seg_len = min(p.n_tiles, seg_lo + p.seg_tiles) - seg_lo;
+            it = 0;
             first = true;
         }
-        last = cur + 1 == tile_hi;
-        n0 = cur * kSearchBN;
+        last = it + 1 == seg_len;
+        const int sub = it / p.sub_tiles;
+        const int sub_lo = sub * p.sub_tiles;
+        const int sub_len = min(p.sub_tiles, seg_len - sub_lo);
+        const int j = it - sub_lo;
+        const int rot = (qg * 5) % sub_len;
+        int t = j + rot;
+        if (t >= sub_len) t -= sub_len;
+        n0 = (seg_lo + sub_lo + t) * kSearchBN;
         return true;
     }
 };
 
 struct SearchPlan {
-    int n_qblocks, n_tiles, n_seg, seg_tiles, n_units, grid;
+    int n_qblocks, n_qgroups, cl, n_tiles, n_seg, seg_tiles, n_units, grid, sub_tiles;
 };
 
 // Pick the segment count that minimises (rounds of units per CTA) x (tiles per unit).
-static SearchPlan make_plan(long long n_rows, int n_query, int n_cta) {
+static SearchPlan make_plan(long long n_rows, int n_query, int n_sm) {
     SearchPlan pl{};
     pl.n_qblocks = (n_query + kBM - 1) / kBM;
+    pl.cl = cluster_size();
+    while (pl.cl > 1 && pl.n_qblocks < pl.cl) pl.cl >>= 1;
+    pl.n_qgroups = (pl.n_qblocks + pl.cl - 1) / pl.cl;
+    const int n_cta = n_sm / pl.cl;  // clusters that fit
     pl.n_tiles = static_cast<int>((n_rows + kSearchBN - 1) / kSearchBN);
     long long best = -1;
     for (int s = 1; s <= kMaxSegments && s <= pl.n_tiles; ++s) {
         const int len = (pl.n_tiles + s - 1) / s;
         const int segs = (pl.n_tiles + len - 1) / len;
-        const long long rounds = (static_cast<long long>(pl.n_qblocks) * segs + n_cta - 1) / n_cta;
+        const long long rounds = (static_cast<long long>(pl.n_qgroups) * segs + n_cta - 1) / n_cta;
         const long long cost = rounds * len + rounds;  // + flush overhead per unit
         if (best < 0 || cost < best) {
             best = cost;
@@ -99,8 +123,13 @@ static SearchPlan make_plan(long long n_rows, int n_query, int n_cta) {
         }
     }
     if (pl.n_tiles == 0) { pl.n_seg = 0; pl.seg_tiles = 1; }
-    pl.n_units = pl.n_qblocks * pl.n_seg;
-    pl.grid = pl.n_units < n_cta ? pl.n_units : n_cta;
+    pl.n_units = pl.n_qgroups * pl.n_seg;
+    pl.grid = (pl.n_units < n_cta ? pl.n_units : n_cta) * pl.cl;
+    // sub-blocks: keep (segments in flight) x (sub-block bytes) around 48 MB of the 126 MB L2
+    const int lanes = pl.n_qblocks > 0 ? (pl.grid + pl.n_qblocks - 1) / pl.n_qblocks : 1;  // segments in flight
+    int sub = 96 / (lanes > 0 ? lanes : 1);  // tiles of 256 rows x 1024 x bf16 = 512 KB
+    if (const char* e = getenv("OFX_SEARCH_SUB_TILES")) sub = atoi(e);
+    pl.sub_tiles = sub < 4 ? 4 : (sub > 64 ? 64 : sub);
     return pl;
 }
 
@@ -115,28 +144,29 @@ struct EpiTopK {
         long long n_rows;
         int n_query;
         uint32_t* thr_enc;         // (n_qblocks * 128) encoded per-query thresholds
-        float* cand_s;             // [n_units][128][KCAP]
+        float* cand_s;             // [n_units][cl][128][KCAP]
         int* cand_i;               // [n_units][128][KCAP] shard-local row ids
         int* cand_n;               // [n_units][128]
     };
     static constexpr int kSmemBytes = KCAP * 128 * 8;
+    static constexpr int kWarps = 4;
 
     float* ls;
     int* li;
-    int cnt, lpos;
-    float lmin, thr;  // accept  s >= thr
+    int cnt, lpos, lidx;
+    float lmin, thr;  // gate: s >= thr (thr = global threshold until the list is full, then its minimum)
     bool full;
 
     __device__ void begin(const Params&, const SchedSearch&, int quarter, int lane, uint8_t* smem) {
         const int t = quarter * 32 + lane;
         ls = reinterpret_cast<float*>(smem) + t;
         li = reinterpret_cast<int*>(smem + KCAP * 128 * 4) + t;
-        cnt = 0; lpos = 0; lmin = 0.f; thr = -INFINITY; full = false;
+        cnt = 0; lpos = 0; lidx = 0; lmin = 0.f; thr = -INFINITY; full = false;
     }
 
     // evict candidate = lowest score, highest index among equal scores.  Static + by-value so
     // the per-thread state stays in registers (no `this` escaping into local memory).
-    static __device__ __noinline__ float2 find_evict(const float* ls, const int* li) {
+    static __device__ __noinline__ float4 find_evict(const float* ls, const int* li) {
         float mn = ls[0];
         int mi = li[0], mp = 0;
 #pragma unroll 8
@@ -145,21 +175,24 @@ struct EpiTopK {
             const int i = li[j * 128];
             if (s < mn || (s == mn && i > mi)) { mn = s; mi = i; mp = j; }
         }
-        return make_float2(mn, __int_as_float(mp));
+        return make_float4(mn, __int_as_float(mp), __int_as_float(mi), 0.f);
     }
     __device__ __forceinline__ void rescan() {
-        const float2 r = find_evict(ls, li);
+        const float4 r = find_evict(ls, li);
         lmin = r.x;
         lpos = __float_as_int(r.y);
-        thr = next_up(r.x);
+        lidx = __float_as_int(r.z);
+        thr = r.x;
     }
 
+    // Tiles of a unit arrive in rotated order, so ties are resolved on the index explicitly:
+    // a full list takes s only if (s, idx) beats its worst entry under (score desc, index asc).
     __device__ __forceinline__ void insert(float s, int idx) {
         if (!full) {
             ls[cnt * 128] = s;
             li[cnt * 128] = idx;
             if (++cnt == KCAP) { full = true; rescan(); }
-        } else {
+        } else if (s > lmin || idx < lidx) {
             ls[lpos * 128] = s;
             li[lpos * 128] = idx;
             rescan();
@@ -206,7 +239,7 @@ struct EpiTopK {
             }
         }
         if (s.last) {
-            const long long slot = static_cast<long long>(s.unit) * 128 + quarter * 32 + lane;
+            const long long slot = (static_cast<long long>(s.unit) * s.p.cl + s.rank) * 128 + quarter * 32 + lane;
             const int n = live ? cnt : 0;
             for (int j = 0; j < n; ++j) {
                 p.cand_s[slot * KCAP + j] = ls[j * 128];
@@ -262,7 +295,7 @@ struct MergeArgs {
     const float* cand_s;
     const int* cand_i;
     const int* cand_n;
-    int kcap, n_seg, n_qblocks, n_pad;  // n_pad = pow2 >= n_seg * kcap
+    int kcap, n_seg, n_qgroups, cl, n_pad;  // n_pad = pow2 >= n_seg * kcap
     const float* queries;       // (nq, dim) fp32
     const float* gallery_f32;   // (n_rows, dim) fp32 or nullptr (no re-rank: bf16-pass scores)
     int dim, metric, k;
@@ -289,7 +322,7 @@ merge_rerank_kernel(const MergeArgs a) {
         const int seg = e / a.kcap, j = e - seg * a.kcap;
         unsigned long long key = 0ull;
         if (seg < a.n_seg) {
-            const long long slot = (static_cast<long long>(seg) * a.n_qblocks + qb) * 128 + r;
+            const long long slot = ((static_cast<long long>(seg) * a.n_qgroups + qb / a.cl) * a.cl + qb % a.cl) * 128 + r;
             if (j < a.cand_n[slot]) {
                 const float s = a.cand_s[slot * a.kcap + j];
                 const uint32_t idx = static_cast<uint32_t>(a.cand_i[slot * a.kcap + j]);
@@ -425,9 +458,9 @@ static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     w.plan = make_plan(n_rows, n_query, sm_count());
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
-    const size_t slots = static_cast<size_t>(w.plan.n_units) * 128;
+    const size_t slots = static_cast<size_t>(w.plan.n_units) * w.plan.cl * 128;
     w.q_bf16 = take(static_cast<size_t>(n_query) * dim * 2);
-    w.thr = take(static_cast<size_t>(w.plan.n_qblocks) * 128 * 4);
+    w.thr = take(static_cast<size_t>(w.plan.n_qgroups) * w.plan.cl * 128 * 4);
     w.cand_n = take(slots * 4);
     w.cand_s = take(slots * w.kcap * 4);
     w.cand_i = take(slots * w.kcap * 4);
@@ -435,21 +468,48 @@ static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     return w;
 }
 
-template <int KCAP, int STAGES>
-static int launch_search(const CUtensorMap& tm_q, const CUtensorMap& tm_g, const SearchPlan& pl,
-                         const typename EpiTopK<KCAP>::Params& ep, int dim, cudaStream_t stream) {
+template <int KCAP, int STAGES, int CL>
+static int launch_search(const void* q_bf16, int n_query, const void* gallery, long long n_rows,
+                         const SearchPlan& pl, const typename EpiTopK<KCAP>::Params& ep, int dim,
+                         cudaStream_t stream) {
     using Epi = EpiTopK<KCAP>;
-    auto kern = tc_kernel<kSearchBN, STAGES, SchedSearch, Epi>;
+    CUtensorMap tm_q, tm_g;
+    OFX_TRY(make_tmap_bf16(&tm_q, q_bf16, static_cast<uint64_t>(n_query), dim, dim, kBM));
+    OFX_TRY(make_tmap_bf16(&tm_g, gallery, static_cast<uint64_t>(n_rows), dim, dim, kSearchBN / CL));
+    auto kern = tc_kernel<kSearchBN, STAGES, CL, SchedSearch, Epi>;
     constexpr int smem = tc_smem_bytes<kSearchBN, STAGES, Epi>();
     static bool configured = false;
     if (!configured) {
         OFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    SchedSearch::Params sp{pl.n_qblocks, pl.n_tiles, pl.seg_tiles, pl.n_units};
-    kern<<<pl.grid, kTcThreads, smem, stream>>>(tm_q, tm_g, sp, ep, dim / kBK);
-    OFX_LAUNCH_CHECK();
+    SchedSearch::Params sp{pl.n_qgroups, pl.n_tiles, pl.seg_tiles, pl.n_units, pl.sub_tiles, CL};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(tc_threads<Epi>());
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    count_launch();
+    OFX_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_q, tm_g, sp, ep, dim / kBK));
     return OFX_OK;
+}
+
+template <int KCAP, int STAGES>
+static int launch_search_cl(const void* q_bf16, int n_query, const void* gallery, long long n_rows,
+                            const SearchPlan& pl, const typename EpiTopK<KCAP>::Params& ep, int dim,
+                            cudaStream_t stream) {
+    switch (pl.cl) {
+        case 4: return launch_search<KCAP, STAGES, 4>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
+        case 2: return launch_search<KCAP, STAGES, 2>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
+        default: return launch_search<KCAP, STAGES, 1>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
+    }
 }
 
 }  // namespace ofx
@@ -518,22 +578,19 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
         const long long nq_el = static_cast<long long>(n_query) * dim;
         to_bf16_kernel<<<static_cast<unsigned>((nq_el / 4 + 255) / 256), 256, 0, st>>>(queries, nq_el, q_bf16);
         OFX_LAUNCH_CHECK();
-        OFX_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(W.plan.n_qblocks) * 128 * 4, st));
-        CUtensorMap tm_q, tm_g;
-        OFX_TRY(make_tmap_bf16(&tm_q, q_bf16, static_cast<uint64_t>(n_query), dim, dim, kBM));
-        OFX_TRY(make_tmap_bf16(&tm_g, pk, static_cast<uint64_t>(n_rows), dim, dim, kSearchBN));
+        OFX_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(W.plan.n_qgroups) * W.plan.cl * 128 * 4, st));
         const float* half = metric == OFX_METRIC_L2 ? reinterpret_cast<const float*>(pk + L.rows_bytes) : nullptr;
         if (W.kcap == 32) {
             EpiTopK<32>::Params ep{half, n_rows, n_query, thr, cand_s, cand_i, cand_n};
-            OFX_TRY((launch_search<32, 4>(tm_q, tm_g, W.plan, ep, dim, st)));
+            OFX_TRY((launch_search_cl<32, 4>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         } else {
             EpiTopK<64>::Params ep{half, n_rows, n_query, thr, cand_s, cand_i, cand_n};
-            OFX_TRY((launch_search<64, 3>(tm_q, tm_g, W.plan, ep, dim, st)));
+            OFX_TRY((launch_search_cl<64, 3>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         }
     }
     MergeArgs ma{};
     ma.cand_s = cand_s; ma.cand_i = cand_i; ma.cand_n = cand_n;
-    ma.kcap = W.kcap; ma.n_seg = W.plan.n_seg; ma.n_qblocks = W.plan.n_qblocks;
+    ma.kcap = W.kcap; ma.n_seg = W.plan.n_seg; ma.n_qgroups = W.plan.n_qgroups; ma.cl = W.plan.cl;
     int n_pad = 2;
     while (n_pad < W.plan.n_seg * W.kcap) n_pad <<= 1;
     ma.n_pad = n_pad;

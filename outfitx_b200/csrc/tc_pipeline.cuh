@@ -7,9 +7,18 @@
 //   warp 0      TMA producer   (one lane): global -> 128B-swizzled smem ring, mbarrier tx
 //   warp 1      MMA issuer     (one lane): tcgen05.mma kind::f16, M=128, N=BN, K=16 x4 / stage
 //   warp 2      TMEM allocator (2*BN fp32 columns = two accumulator buffers)
-//   warps 4..7  epilogue       (thread t <-> accumulator row t): tcgen05.ld + Epi::tile()
+//   warps 4..   epilogue       Epi::kWarps = 4 or 8 warps; warp w reads TMEM lanes 32*(w%4)..+31
+//                              (hardware rule), so with 8 warps two warps share a row quarter
+//                              and split the tile's columns: tcgen05.ld + Epi::tile()
 // Three barrier rings: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 // The tile sequence comes from a Sched object that all roles evaluate identically.
+//
+// CL > 1: thread-block clusters of CL CTAs that work on the SAME B tile (n0) with different A
+// tiles (m0).  Each CTA fetches 1/CL of the B tile and TMA-multicasts it into every CTA of the
+// cluster, so a B tile crosses the L2 -> SM fabric once per cluster instead of once per CTA.
+// A stage may be refilled only when every CTA of the cluster has consumed it (all of them are
+// written by each multicast), hence empty barriers count CL arrivals and the MMA commit is
+// multicast to all CTAs.  The Sched must give all CTAs of a cluster the same tile count and n0.
 #pragma once
 #include <cuda.h>
 
@@ -20,7 +29,6 @@ namespace ofx {
 constexpr int kBM = 128;       // accumulator rows per CTA tile (UMMA M, cta_group::1)
 constexpr int kBK = 64;        // bf16 elements per smem row = 128 B = one swizzle span
 constexpr int kUmmaK = 16;     // K per tcgen05.mma for 16-bit inputs
-constexpr int kTcThreads = 256;
 constexpr int kEpiWarp0 = 4;   // first epilogue warp (warp % 4 selects the TMEM lane quarter)
 
 template <int BN, int STAGES>
@@ -46,12 +54,17 @@ constexpr int tc_smem_bytes() {
 //   int m0, n0;                      tile origin (rows of A, rows of B)
 // Epi concept:
 //   struct Params; static constexpr int kSmemBytes;
-//   __device__ void begin(const Params&, const Sched&, int quarter, int lane, uint8_t* smem);
-//   __device__ void tile(const Params&, const Sched&, uint32_t tmem_acc,
-//                        int quarter /*0..3*/, int lane, uint8_t* epi_smem);
+//   static constexpr int kWarps;   4 or 8 epilogue warps
+//   __device__ void begin(const Params&, const Sched&, int ewarp, int lane, uint8_t* smem);
+//   __device__ void tile(const Params&, const Sched&, uint32_t tmem_acc /*lane quarter applied*/,
+//                        int ewarp /*0..kWarps-1: quarter = ewarp & 3, column group = ewarp >> 2*/,
+//                        int lane, uint8_t* epi_smem);
 //   (an object per epilogue thread: state such as running top-k thresholds lives in it)
-template <int BN, int STAGES, class Sched, class Epi>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <class Epi>
+constexpr int tc_threads() { return 128 + 32 * Epi::kWarps; }
+
+template <int BN, int STAGES, int CL, class Sched, class Epi>
+__global__ void __launch_bounds__(128 + 32 * Epi::kWarps, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
           const typename Sched::Params sp, const typename Epi::Params ep, const int num_k_blocks) {
     using Cfg = TcCfg<BN, STAGES>;
@@ -71,6 +84,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
+    constexpr int kBRowsPerCta = BN / CL;  // rows of the B tile this CTA fetches
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -79,17 +95,18 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], CL);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], Epi::kWarps);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any remote use
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -104,7 +121,12 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
                     tma_load_2d(s_a + stage * Cfg::kABytes, &tm_a, &full[stage], kb * kBK, sched.m0);
-                    tma_load_2d(s_b + stage * Cfg::kBBytes, &tm_b, &full[stage], kb * kBK, sched.n0);
+                    if constexpr (CL == 1) {
+                        tma_load_2d(s_b + stage * Cfg::kBBytes, &tm_b, &full[stage], kb * kBK, sched.n0);
+                    } else {
+                        tma_load_2d_mc(s_b + stage * Cfg::kBBytes + crank * (kBRowsPerCta * kBK * 2), &tm_b,
+                                       &full[stage], kb * kBK, sched.n0 + crank * kBRowsPerCta, kAllCtas);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -131,7 +153,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                                   umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc,
                                   (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);  // frees the smem slot when the MMAs retire
+                    // frees the smem slot (in every CTA of the cluster) when the MMAs retire
+                    if constexpr (CL == 1) umma_commit(&empty[stage]);
+                    else umma_commit_mc(&empty[stage], kAllCtas);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
@@ -140,17 +164,18 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         }
     } else if (warp >= kEpiWarp0) {
         // ------------------------------------------------------------ epilogue
+        const int ewarp = warp - kEpiWarp0;
         const int quarter = warp & 3;
         Sched sched(sp, blockIdx.x, gridDim.x);
         int acc = 0;
         uint32_t acc_phase = 0;
         Epi epi;
-        epi.begin(ep, sched, quarter, lane, epi_smem);
+        epi.begin(ep, sched, ewarp, lane, epi_smem);
         while (sched.next()) {
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-            epi.tile(ep, sched, t_acc, quarter, lane, epi_smem);
+            epi.tile(ep, sched, t_acc, ewarp, lane, epi_smem);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -159,6 +184,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);

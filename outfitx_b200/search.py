@@ -148,8 +148,9 @@ class ShardedSearch:
             return idx, score
         # one collective: ids and the fp64 scores' bit patterns travel as one int64 payload
         payload = torch.stack([idx, score.view(torch.int64)]).contiguous()       # (2, nq, k)
-        gathered = torch.empty((world,) + tuple(payload.shape), dtype=torch.int64, device=idx.device)
-        dist.all_gather_into_tensor(gathered, payload, group=self.group)
+        gathered = torch.empty((world * 2,) + tuple(idx.shape), dtype=torch.int64, device=idx.device)
+        dist.all_gather_into_tensor(gathered, payload, group=self.group)   # concatenated along dim 0
+        gathered = gathered.view((world, 2) + tuple(idx.shape))
         all_i = gathered[:, 0].contiguous()
         all_s = gathered[:, 1].contiguous().view(torch.float64)
         return self._merge(all_i, all_s, k)
