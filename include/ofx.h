@@ -174,6 +174,15 @@ OFX_API int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw
                   int32_t k, const float* bias, int32_t act_mish, const float* residual,
                   int64_t ldr, void* out, int64_t ldo, int32_t out_f32, void* stream);
 
+/* ---- building block exported for tests / profiling: the fused feed-forward block of one
+ * encoder layer,  x <- x + W2 . mish(W1 . LayerNorm(x) + b1) + b2  in place on the fp32 rows
+ * (torch TransformerEncoderLayer._ff_block as configured at outfit_x.py:32-45).
+ * x (rows, d_model) fp32; w1 (d_ffn_padded, d_model) bf16; w2 (d_model, d_ffn_padded) bf16;
+ * b1 (d_ffn_padded), b2 / ln_w / ln_b (d_model) fp32.  d_model == 512, d_ffn_padded % 256 == 0. */
+OFX_API int ofx_ffn_block_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_padded,
+                       const float* ln_w, const float* ln_b, const void* w1, const float* b1,
+                       const void* w2, const float* b2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

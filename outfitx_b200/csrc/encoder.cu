@@ -3,6 +3,8 @@
 // Mirrors OutfitX._cp_forward / _cir_forward (/root/reference/src/models/outfit_x.py:120-172)
 // with the exact simplifications of SURVEY.md App. A.4: padded tokens dropped, last layer
 // evaluated for the prefix-token query row only.
+#include <stdlib.h>
+
 #include "encoder_ops.h"
 #include "gemm.h"
 
@@ -117,6 +119,16 @@ static WsLayout make_ws(const ofx_shape* s, int batch) {
     return W;
 }
 
+// OFX_FUSED_FFN=0 falls back to LN + two separate GEMMs (for A/B timing; same results within bf16 noise)
+static bool fused_ffn_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("OFX_FUSED_FFN");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 template <class T> static int gemm(const GemmArgs& g, cudaStream_t st);
 template <> int gemm<float>(const GemmArgs& g, cudaStream_t st) { return gemm_f32(g, st); }
 template <> int gemm<__nv_bfloat16>(const GemmArgs& g, cudaStream_t st) { return gemm_bf16(g, st); }
@@ -138,6 +150,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
     T* u0 = reinterpret_cast<T*>(ws + W.u0);
     auto lw = [&](int l, size_t o) { return wts + L.layer_bytes * l + o; };
     auto lf = [&](int l, size_t o) { return reinterpret_cast<const float*>(lw(l, o)); };
+    const bool fused_ffn = sizeof(T) == 2 && ffn_block_supported(dm, fp) && fused_ffn_enabled();
 
     OFX_TRY(scan_valid(a->mask, B, s->max_items, off, n_tok, st));
     AssembleArgs as{};
@@ -169,11 +182,17 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
             OFX_TRY(attention<T>(at, hd, st));
             GemmArgs go{h, dm, lw(l, L.w_o), dm, W.t_max, n_tok, dm, dm, lf(l, L.b_o), 0, x, dm, x, dm, 1};
             OFX_TRY(gemm<T>(go, st));
-            OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
-            GemmArgs g1{h, dm, lw(l, L.w_1), dm, W.t_max, n_tok, fp, dm, lf(l, L.b_1), 1, nullptr, 0, big, fp, 0};
-            OFX_TRY(gemm<T>(g1, st));
-            GemmArgs g2{big, fp, lw(l, L.w_2), fp, W.t_max, n_tok, dm, fp, lf(l, L.b_2), 0, x, dm, x, dm, 1};
-            OFX_TRY(gemm<T>(g2, st));
+            if (fused_ffn) {
+                FfnBlockArgs fa{x, W.t_max, n_tok, dm, fp, lf(l, L.ln2w), lf(l, L.ln2b), lw(l, L.w_1),
+                                lf(l, L.b_1), lw(l, L.w_2), lf(l, L.b_2)};
+                OFX_TRY(ffn_block_bf16(fa, st));
+            } else {
+                OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
+                GemmArgs g1{h, dm, lw(l, L.w_1), dm, W.t_max, n_tok, fp, dm, lf(l, L.b_1), 1, nullptr, 0, big, fp, 0};
+                OFX_TRY(gemm<T>(g1, st));
+                GemmArgs g2{big, fp, lw(l, L.w_2), fp, W.t_max, n_tok, dm, fp, lf(l, L.b_2), 0, x, dm, x, dm, 1};
+                OFX_TRY(gemm<T>(g2, st));
+            }
         } else {
             // last layer: K,V for every token, everything else for the prefix row only
             const T* w_in = reinterpret_cast<const T*>(lw(l, L.w_qkv));
@@ -188,11 +207,17 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
             OFX_TRY(attention<T>(at, hd, st));
             GemmArgs go{a0, dm, lw(l, L.w_o), dm, B, nullptr, dm, dm, lf(l, L.b_o), 0, x, dm, x, dm, 1};
             OFX_TRY(gemm<T>(go, st));
-            OFX_TRY(layernorm<T>(x, B, nullptr, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
-            GemmArgs g1{h, dm, lw(l, L.w_1), dm, B, nullptr, fp, dm, lf(l, L.b_1), 1, nullptr, 0, u0, fp, 0};
-            OFX_TRY(gemm<T>(g1, st));
-            GemmArgs g2{u0, fp, lw(l, L.w_2), fp, B, nullptr, dm, fp, lf(l, L.b_2), 0, x, dm, x, dm, 1};
-            OFX_TRY(gemm<T>(g2, st));
+            if (fused_ffn) {
+                FfnBlockArgs fa{x, B, nullptr, dm, fp, lf(l, L.ln2w), lf(l, L.ln2b), lw(l, L.w_1),
+                                lf(l, L.b_1), lw(l, L.w_2), lf(l, L.b_2)};
+                OFX_TRY(ffn_block_bf16(fa, st));
+            } else {
+                OFX_TRY(layernorm<T>(x, B, nullptr, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
+                GemmArgs g1{h, dm, lw(l, L.w_1), dm, B, nullptr, fp, dm, lf(l, L.b_1), 1, nullptr, 0, u0, fp, 0};
+                OFX_TRY(gemm<T>(g1, st));
+                GemmArgs g2{u0, fp, lw(l, L.w_2), fp, B, nullptr, dm, fp, lf(l, L.b_2), 0, x, dm, x, dm, 1};
+                OFX_TRY(gemm<T>(g2, st));
+            }
         }
     }
     if (a->task == OFX_TASK_CP) {
@@ -288,5 +313,17 @@ int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int32_
     OFX_TRY(require_sm100());
     GemmArgs g{a, lda, w, ldw, m, nullptr, n, k, bias, act_mish, residual, ldr, out, ldo, out_f32};
     return gemm_bf16(g, static_cast<cudaStream_t>(stream));
+}
+
+int ofx_ffn_block_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_padded, const float* ln_w,
+                       const float* ln_b, const void* w1, const float* b1, const void* w2, const float* b2,
+                       void* stream) {
+    if (!x || !ln_w || !ln_b || !w1 || !b1 || !w2 || !b2) return fail(OFX_E_ARG, "ofx_ffn_block_bf16: null argument");
+    if (rows < 0) return fail(OFX_E_SHAPE, "ofx_ffn_block_bf16: rows %d", rows);
+    if (!ffn_block_supported(d_model, d_ffn_padded))
+        return fail(OFX_E_SHAPE, "ofx_ffn_block_bf16: needs d_model 512 and d_ffn_padded %% 256 == 0");
+    OFX_TRY(require_sm100());
+    FfnBlockArgs fa{x, rows, nullptr, d_model, d_ffn_padded, ln_w, ln_b, w1, b1, w2, b2};
+    return ffn_block_bf16(fa, static_cast<cudaStream_t>(stream));
 }
 }

@@ -31,6 +31,22 @@ struct AttnArgs {
     void* out; long long ldo;
 };
 
+// fused LN2 -> linear1 -> mish -> linear2 -> +residual on the fp32 residual stream (ffn_block.cu)
+struct FfnBlockArgs {
+    float* x;              // (rows, dm) fp32, updated in place
+    int rows;              // host upper bound
+    const int* rows_dev;   // optional device-side row count
+    int dm, fp;            // d_model, padded d_ffn
+    const float* ln_w;     // norm2
+    const float* ln_b;
+    const void* w1;        // (fp, dm) bf16
+    const float* b1;       // (fp)
+    const void* w2;        // (dm, fp) bf16
+    const float* b2;       // (dm)
+};
+bool ffn_block_supported(int dm, int fp);
+int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream);
+
 int scan_valid(const uint8_t* mask, int batch, int max_items, int* off, int* n_tok, cudaStream_t stream);
 int fuse_rows(const float* img, const float* txt, long long rows, int dpm, int mode, int normalize,
               float* out, cudaStream_t stream);

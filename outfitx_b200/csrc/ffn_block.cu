@@ -1,0 +1,436 @@
+// Fused feed-forward block of one encoder layer (d_model 512), one kernel:
+//
+//     x  <-  x + W2 . mish(W1 . LN2(x) + b1) + b2            (rows of the token matrix, in place)
+//
+// i.e. torch.nn.TransformerEncoderLayer's `x = x + _ff_block(norm2(x))` (pre-LN slow path,
+// torch/nn/modules/transformer.py:950,980-982) as the reference builds it at
+// /root/reference/src/models/outfit_x.py:32-45 (activation = F.mish, d_ffn 2024 zero-padded to 2048).
+// The 2048-wide hidden activation never leaves the SM: it goes TMEM -> registers (bias + mish)
+// -> shared memory (bf16, UMMA operand layout) -> second GEMM.  HBM traffic per token is one
+// fp32 row in and one out (4 KB) instead of the 16 KB of LN + two separate GEMMs.
+//
+// Work decomposition: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns 128 consecutive
+// token rows, 64 per CTA.  With M = 128 across the pair an accumulator of 64 rows x N columns
+// occupies 128 TMEM lanes x N/2 columns per CTA, so the full-width output (64 x 512 fp32 =
+// 256 columns) and two 64 x 256 hidden-chunk accumulators (2 x 128 columns) fit the 512 TMEM
+// columns together -- with cta_group::1 (128 rows per CTA) the output tile alone fills TMEM.
+// Weight tiles are split across the pair (each CTA loads half of the N rows of every B tile),
+// so every weight byte crosses L2 -> SM once per 128 token rows.
+//
+// Per tile the hidden dimension is swept in chunks of 256 units:
+//   G1(c): acc1[c&1] = H . W1[c]^T          8 k-blocks of 64, N = 256
+//   E (c): U[c&1] = bf16(mish(acc1 + b1))   epilogue warps, TMEM -> smem
+//   G2(c): acc2 += U[c&1] . W2[:, c]^T      4 k-blocks of 64, 2 x (N = 256)
+// issued as G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... so the tensor pipe always has one
+// GEMM phase of work queued while the epilogue of a chunk runs.
+//
+// Warp roles (16 warps): 0 TMA producer (weights), 1 MMA issuer (leader CTA only), 2 TMEM
+// allocator, 4-11 epilogue (mish chunks, then the residual epilogue), 12-15 LayerNorm prologue
+// (x rows -> H in the swizzled K-major operand layout).
+#include <cuda.h>
+
+#include "encoder_ops.h"
+#include "ptx.cuh"
+
+namespace ofx {
+namespace ffnb {
+
+constexpr int DM = 512;               // d_model (K of GEMM 1, N of GEMM 2)
+constexpr int KB1 = DM / 64;          // k-blocks of GEMM 1
+constexpr int CH = 256;               // hidden units per chunk (N of GEMM 1)
+constexpr int KB2 = CH / 64;          // k-blocks of GEMM 2 per chunk
+constexpr int ROWS = 64;              // token rows per CTA
+constexpr int TILE = 2 * ROWS;        // token rows per CTA pair
+constexpr int KBLK_BYTES = ROWS * 128;        // one 64-row x 64-element bf16 operand block
+constexpr int H_BYTES = KB1 * KBLK_BYTES;     // 64 KB
+constexpr int U_BYTES = KB2 * KBLK_BYTES;     // 32 KB
+constexpr int STAGE_BYTES = 128 * 128;        // 128 weight rows x 64 K per CTA per stage
+constexpr int NSTAGE = 6;
+constexpr int BAR_BYTES = 512;
+constexpr int SMEM_BYTES = 1024 + H_BYTES + 2 * U_BYTES + NSTAGE * STAGE_BYTES + BAR_BYTES;
+constexpr int NTHREADS = 512;
+constexpr int EPI_WARP0 = 4, N_EPI_WARPS = 8, LN_WARP0 = 12, N_LN_WARPS = 4;
+constexpr uint32_t TM_ACC1 = 0, TM_ACC2 = 256;  // TMEM columns
+
+struct Params {
+    float* x;               // (rows, 512) fp32 residual stream, updated in place
+    int rows;               // host-side row count (upper bound when rows_dev != nullptr)
+    const int* rows_dev;    // optional device-side row count
+    const float* ln_w;      // LayerNorm 2
+    const float* ln_b;
+    const float* b1;        // (n_chunks * 256) fp32, zero beyond d_ffn
+    const float* b2;        // (512)
+    int n_chunks;           // padded d_ffn / 256
+};
+
+__device__ __forceinline__ float mish_fast(float x) {
+    // x * n / (n + 2), n = w (w + 2), w = e^x   (see gemm.cu)
+    float w, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(fminf(x, 40.f) * 1.4426950408889634f));
+    const float n = fmaf(w, w, w + w);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.f));
+    return x * n * r;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+                 const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* s_h = smem;
+    uint8_t* s_u = smem + H_BYTES;                       // U[0], U[1]
+    uint8_t* s_w = smem + H_BYTES + 2 * U_BYTES;         // weight ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + NSTAGE * STAGE_BYTES);
+    uint64_t* w_full = bars;                    // [NSTAGE]  leader's are used (tx from both CTAs)
+    uint64_t* w_empty = bars + NSTAGE;          // [NSTAGE]  per CTA (multicast commit)
+    uint64_t* acc1_full = bars + 2 * NSTAGE;    // [2]       per CTA (multicast commit)
+    uint64_t* u_full = acc1_full + 2;           // [2]       leader's: 16 epilogue-warp arrivals
+    uint64_t* acc2_full = u_full + 2;           //           per CTA (multicast commit)
+    uint64_t* acc2_empty = acc2_full + 1;       //           leader's: 16 arrivals
+    uint64_t* h_full = acc2_empty + 1;          //           leader's: 8 LN-warp arrivals
+    uint64_t* h_empty = h_full + 1;             //           per CTA (multicast commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_rows = p.rows_dev ? min(*p.rows_dev, p.rows) : p.rows;
+    const int n_tiles = (n_rows + TILE - 1) / TILE;
+    const int nch = p.n_chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_w1);
+        tma_prefetch_desc(&tm_w2);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&w_full[i], 1);
+            mbar_init(&w_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc1_full[i], 1);
+            mbar_init(&u_full[i], 2 * N_EPI_WARPS);
+        }
+        mbar_init(acc2_full, 1);
+        mbar_init(acc2_empty, 2 * N_EPI_WARPS);
+        mbar_init(h_full, 2 * N_LN_WARPS);
+        mbar_init(h_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (weights)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int r128 = static_cast<int>(rank) * 128;
+            auto put = [&](const CUtensorMap* tm, int c_inner, int c_outer) {
+                mbar_wait(&w_empty[stage], phase ^ 1);
+                if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
+                tma_load_2d_pair(s_w + stage * STAGE_BYTES, tm, mapa_shared(smem_u32(&w_full[stage]), 0),
+                                 c_inner, c_outer, kEvictLast);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            };
+            auto g1 = [&](int c) {
+                for (int kb = 0; kb < KB1; ++kb) put(&tm_w1, kb * 64, c * CH + r128);
+            };
+            auto g2 = [&](int c) {
+                for (int kb = 0; kb < KB2; ++kb)
+                    for (int half = 0; half < 2; ++half) put(&tm_w2, c * CH + kb * 64, half * 256 + r128);
+            };
+            for (int t = pair; t < n_tiles; t += n_pairs) {
+                g1(0);
+                if (nch > 1) g1(1);
+                for (int c = 0; c < nch; ++c) {
+                    g2(c);
+                    if (c + 2 < nch) g1(c + 2);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader only)
+        // The whole warp runs the loop (warp-uniform control flow and addresses, so the
+        // descriptors live in uniform registers); one elected lane issues the tcgen05 ops.
+        // An M=128 / N=256 pair MMA occupies the tensor pipe for only 64 cycles, so the issue
+        // path has to stay within a handful of instructions per MMA.
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SW128
+            const uint32_t h_lo = ((smem_u32(s_h) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t u_lo = ((smem_u32(s_u) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t w_lo = ((smem_u32(s_w) & 0x3FFFF) >> 4) | (1u << 16);
+            auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0, uph0 = 0, uph1 = 0;
+            auto g1 = [&](int c) {
+                const uint32_t d = tmem_base + TM_ACC1 + (c & 1) * 128;
+                for (int kb = 0; kb < KB1; ++kb) {
+                    mbar_wait(&w_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a = h_lo + kb * (KBLK_BYTES >> 4);
+                    const uint32_t b = w_lo + stage * (STAGE_BYTES >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_pair(d, desc(a + 2 * k), desc(b + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair(&w_empty[stage], 0b11);
+                    }
+                    __syncwarp();
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                if (elect_one()) {
+                    umma_commit_pair(&acc1_full[c & 1], 0b11);
+                    if (c == nch - 1) umma_commit_pair(h_empty, 0b11);   // H may be refilled
+                }
+                __syncwarp();
+            };
+            auto g2 = [&](int c) {
+                if (c & 1) { mbar_wait_cluster(&u_full[1], uph1); uph1 ^= 1; }
+                else       { mbar_wait_cluster(&u_full[0], uph0); uph0 ^= 1; }
+                tc_fence_after();
+                const uint32_t ub = u_lo + (c & 1) * (U_BYTES >> 4);
+                for (int kb = 0; kb < KB2; ++kb) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        mbar_wait(&w_full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a = ub + kb * (KBLK_BYTES >> 4);
+                        const uint32_t b = w_lo + stage * (STAGE_BYTES >> 4);
+                        const uint32_t d = tmem_base + TM_ACC2 + half * 128;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_pair(d, desc(a + 2 * k), desc(b + 2 * k), idesc, (c | kb | k) != 0 ? 1u : 0u);
+                            umma_commit_pair(&w_empty[stage], 0b11);
+                        }
+                        __syncwarp();
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                }
+            };
+            for (int t = pair; t < n_tiles; t += n_pairs) {
+                mbar_wait_cluster(h_full, tphase);
+                tc_fence_after();
+                g1(0);
+                if (nch > 1) g1(1);
+                for (int c = 0; c < nch; ++c) {
+                    if (c == 0) {   // the previous tile's output has left TMEM
+                        mbar_wait_cluster(acc2_empty, tphase ^ 1);
+                        tc_fence_after();
+                    }
+                    g2(c);
+                    if (c + 2 < nch) g1(c + 2);
+                }
+                if (elect_one()) umma_commit_pair(acc2_full, 0b11);
+                __syncwarp();
+                tphase ^= 1;
+            }
+        }
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + N_EPI_WARPS) {
+        // ------------------------------------------------------------ epilogue warps
+        const int q = warp & 3;                       // TMEM lane quarter
+        const int ch = (warp - EPI_WARP0) >> 2;       // which 64 of the accumulator's 128 columns
+        const int row_l = (q & 1) * 32 + lane;        // token row within this CTA's 64
+        const int nhalf = q >> 1;                     // N half held by lanes 64..127
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int kblk = nhalf * 2 + ch;              // k-block of U this thread's 64 values form
+        const uint32_t u_row = kblk * KBLK_BYTES + (row_l >> 3) * 1024 + (row_l & 7) * 128;
+        const int sw = row_l & 7;
+        const uint32_t ufull0 = mapa_shared(smem_u32(&u_full[0]), 0);
+        const uint32_t ufull1 = mapa_shared(smem_u32(&u_full[1]), 0);
+        const uint32_t a2empty = mapa_shared(smem_u32(acc2_empty), 0);
+        // staging for the residual epilogue: this warp's own 32-row x 128-byte block of U[0]
+        uint8_t* stg = s_u + kblk * KBLK_BYTES + (q & 1) * 4096;
+        const int sub_row = lane >> 3, chunk = lane & 7;
+        uint32_t a1ph[2] = {0, 0}, tphase = 0;
+        for (int t = pair; t < n_tiles; t += n_pairs) {
+            for (int c = 0; c < nch; ++c) {
+                const int b = c & 1;
+                mbar_wait(&acc1_full[b], a1ph[b]);
+                a1ph[b] ^= 1;
+                tc_fence_after();
+                const float* bias = p.b1 + c * CH + nhalf * 128 + ch * 64;
+                uint8_t* dst = s_u + b * U_BYTES + u_row;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(t_lane + TM_ACC1 + b * 128 + ch * 64 + s * 32, raw);
+                    float4 bv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + s * 32) + i);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float4 bb = bv[2 * j + h];
+                            const float v0 = mish_fast(__uint_as_float(raw[8 * j + 4 * h + 0]) + bb.x);
+                            const float v1 = mish_fast(__uint_as_float(raw[8 * j + 4 * h + 1]) + bb.y);
+                            const float v2 = mish_fast(__uint_as_float(raw[8 * j + 4 * h + 2]) + bb.z);
+                            const float v3 = mish_fast(__uint_as_float(raw[8 * j + 4 * h + 3]) + bb.w);
+                            w[2 * h] = pack_bf16(v0, v1);
+                            w[2 * h + 1] = pack_bf16(v2, v3);
+                        }
+                        *reinterpret_cast<uint4*>(dst + (((s * 4 + j) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                fence_proxy_async();     // generic-proxy smem writes -> visible to the UMMA (async proxy)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(b ? ufull1 : ufull0);
+            }
+            // ---- residual epilogue: x <- x + acc2 + b2 for this warp's 32 rows x 128 columns
+            mbar_wait(acc2_full, tphase);
+            tphase ^= 1;
+            tc_fence_after();
+            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + (q & 1) * 32;
+            const int rows_valid = n_rows - static_cast<int>(row0) - sub_row;   // row 4i+sub_row live iff 4i < rows_valid
+#pragma unroll 1
+            for (int sl = 0; sl < 4; ++sl) {
+                const int half = sl >> 1, s = sl & 1;
+                const int col0 = half * 256 + nhalf * 128 + ch * 64 + s * 32 + chunk * 4;
+                float* xp = p.x + (row0 + sub_row) * DM + col0;
+                uint32_t raw[32];
+                tmem_ld_32x32(t_lane + TM_ACC2 + half * 128 + ch * 64 + s * 32, raw);
+                float4 res[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    res[i] = 4 * i < rows_valid ? *reinterpret_cast<const float4*>(xp + static_cast<long long>(4 * i) * DM)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col0));
+                tmem_ld_wait();
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+                        make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + sub_row;
+                    float4 v = *reinterpret_cast<const float4*>(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
+                    if (4 * i < rows_valid) {
+                        v.x += b4.x + res[i].x; v.y += b4.y + res[i].y;
+                        v.z += b4.z + res[i].z; v.w += b4.w + res[i].w;
+                        *reinterpret_cast<float4*>(xp + static_cast<long long>(4 * i) * DM) = v;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(a2empty);
+        }
+    } else if (warp >= LN_WARP0) {
+        // ------------------------------------------------------------ LayerNorm prologue: x rows -> H
+        const int lw = warp - LN_WARP0;
+        const uint32_t hfull = mapa_shared(smem_u32(h_full), 0);
+        uint32_t tphase = 0;
+        for (int t = pair; t < n_tiles; t += n_pairs) {
+            mbar_wait(h_empty, tphase ^ 1);     // GEMM 1 of the previous tile has consumed H
+            tphase ^= 1;
+            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 16;
+#pragma unroll 1
+            for (int rb = 0; rb < 16; rb += 4) {
+                float4 v[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long row = row0 + rb + u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        v[u][i] = row < n_rows ? *reinterpret_cast<const float4*>(p.x + row * DM + i * 128 + lane * 4)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s += v[u][i].x + v[u][i].y + v[u][i].z + v[u][i].w;
+                    const float mu = warp_sum(s) * (1.f / DM);
+                    float qq = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float a = v[u][i].x - mu, b = v[u][i].y - mu, c = v[u][i].z - mu, d = v[u][i].w - mu;
+                        qq += a * a + b * b + c * c + d * d;
+                    }
+                    const float rstd = rsqrtf(warp_sum(qq) * (1.f / DM) + 1e-5f);
+                    const int r = lw * 16 + rb + u;      // row within this CTA's 64
+                    const bool live = row0 + rb + u < n_rows;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w + i * 128 + lane * 4));
+                        const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_b + i * 128 + lane * 4));
+                        float y0 = (v[u][i].x - mu) * rstd * g.x + be.x;
+                        float y1 = (v[u][i].y - mu) * rstd * g.y + be.y;
+                        float y2 = (v[u][i].z - mu) * rstd * g.z + be.z;
+                        float y3 = (v[u][i].w - mu) * rstd * g.w + be.w;
+                        if (!live) y0 = y1 = y2 = y3 = 0.f;
+                        // element e = i*128 + lane*4: k-block e/64, 16-byte chunk (e%64)/8, 8-byte half
+                        const int kb = i * 2 + (lane >> 4);
+                        const int c16 = (lane & 15) >> 1;
+                        uint8_t* dst = s_h + kb * KBLK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 +
+                                       ((c16 ^ (r & 7)) << 4) + (lane & 1) * 8;
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(hfull);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+}  // namespace ffnb
+
+bool ffn_block_supported(int dm, int fp) { return dm == ffnb::DM && fp > 0 && fp % ffnb::CH == 0; }
+
+int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
+    using namespace ffnb;
+    if (a.rows <= 0) return OFX_OK;
+    if (a.dm != DM || a.fp <= 0 || a.fp % CH != 0)
+        return fail(OFX_E_SHAPE, "ffn_block: needs d_model 512 and padded d_ffn %% 256 == 0 (got %d, %d)", a.dm, a.fp);
+    CUtensorMap tm_w1, tm_w2;
+    OFX_TRY(make_tmap_bf16(&tm_w1, a.w1, static_cast<uint64_t>(a.fp), DM, DM, 128));
+    OFX_TRY(make_tmap_bf16(&tm_w2, a.w2, DM, static_cast<uint64_t>(a.fp), a.fp, 128));
+    static bool configured = false;
+    if (!configured) {
+        OFX_CUDA(cudaFuncSetAttribute(ffn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int n_tiles = (a.rows + TILE - 1) / TILE;
+    const int max_pairs = sm_count() / 2;
+    const int pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
+    Params p{a.x, a.rows, a.rows_dev, a.ln_w, a.ln_b, a.b1, a.b2, a.fp / CH};
+    ffn_block_kernel<<<pairs * 2, NTHREADS, SMEM_BYTES, stream>>>(tm_w1, tm_w2, p);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+}  // namespace ofx

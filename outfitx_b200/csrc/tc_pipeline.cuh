@@ -133,8 +133,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp walks the schedule (warp-uniform control flow and addresses keep the
+        // descriptors in uniform registers); one elected lane issues the tcgen05 instructions
+        // back to back.  A lane-0-only loop costs ~20 issue slots per MMA in address traffic
+        // between the vector and uniform register files.
+        {
             constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SW128
+            const uint32_t a_lo0 = ((smem_u32(s_a) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = ((smem_u32(s_b) & 0x3FFFF) >> 4) | (1u << 16);
+            auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
             Sched sched(sp, blockIdx.x, gridDim.x);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -145,20 +153,22 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(s_a + stage * Cfg::kABytes);
-                    const uint32_t b_addr = smem_u32(s_b + stage * Cfg::kBBytes);
+                    const uint32_t a_lo = a_lo0 + stage * (Cfg::kABytes >> 4);
+                    const uint32_t b_lo = b_lo0 + stage * (Cfg::kBBytes >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + k * kUmmaK * 2),
-                                  umma_desc_k_sw128(b_addr + k * kUmmaK * 2), idesc,
-                                  (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBK / kUmmaK; ++k)
+                            umma_bf16(d_tmem, desc(a_lo + k * (kUmmaK * 2 >> 4)), desc(b_lo + k * (kUmmaK * 2 >> 4)),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                        // frees the smem slot (in every CTA of the cluster) when the MMAs retire
+                        if constexpr (CL == 1) umma_commit(&empty[stage]);
+                        else umma_commit_mc(&empty[stage], kAllCtas);
                     }
-                    // frees the smem slot (in every CTA of the cluster) when the MMAs retire
-                    if constexpr (CL == 1) umma_commit(&empty[stage]);
-                    else umma_commit_mc(&empty[stage], kAllCtas);
+                    __syncwarp();
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

@@ -1,0 +1,64 @@
+"""GPU: the fused feed-forward block (ofx_ffn_block_bf16: LayerNorm -> linear1 -> mish -> linear2
+-> +residual in one tcgen05 cta_group::2 kernel) against a torch fp32 evaluation of the same
+arithmetic (torch TransformerEncoderLayer._ff_block as the reference configures it,
+/root/reference/src/models/outfit_x.py:32-45), with the operands rounded to bf16 where the
+kernel rounds them (LN output, weights, hidden activation)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DM, FP = 512, 2048
+
+
+def _run(x, ln_w, ln_b, w1, b1, w2, b2):
+    from outfitx_b200 import _lib
+    out = x.clone()
+    _lib.check(_lib.lib().ofx_ffn_block_bf16(
+        out.data_ptr(), out.shape[0], DM, w1.shape[0], ln_w.data_ptr(), ln_b.data_ptr(), w1.data_ptr(),
+        b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return out
+
+
+def _want(x, ln_w, ln_b, w1, b1, w2, b2):
+    h = F.layer_norm(x, (DM,), ln_w, ln_b, 1e-5).to(torch.bfloat16).float()
+    u = F.mish(h @ w1.float().T + b1).to(torch.bfloat16).float()
+    return x + u @ w2.float().T + b2
+
+
+def _params(seed, fp=FP, d_ffn=2024):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    ln_w, ln_b = 1.0 + 0.1 * r(DM), 0.1 * r(DM)
+    w1 = (r(fp, DM) / DM ** 0.5)
+    b1 = 0.1 * r(fp)
+    w2 = (r(DM, fp) / fp ** 0.5)
+    b2 = 0.1 * r(DM)
+    w1[d_ffn:] = 0; b1[d_ffn:] = 0; w2[:, d_ffn:] = 0      # the 2024 -> 2048 zero padding
+    return ln_w, ln_b, w1.to(torch.bfloat16).contiguous(), b1, w2.to(torch.bfloat16).contiguous(), b2, g
+
+
+@pytest.mark.parametrize("rows", [1, 63, 64, 65, 127, 128, 129, 1000, 128 * 74 + 5, 40000])
+def test_ffn_block_matches_fp32(rows):
+    ln_w, ln_b, w1, b1, w2, b2, g = _params(rows)
+    x = torch.randn(rows, DM, device="cuda", generator=g) * 0.7 + 0.05
+    got = _run(x, ln_w, ln_b, w1, b1, w2, b2)
+    want = _want(x, ln_w, ln_b, w1, b1, w2, b2)
+    torch.testing.assert_close(got, want, rtol=6e-3, atol=6e-3)
+
+
+def test_ffn_block_other_chunk_counts():
+    for fp in (256, 512, 1024):
+        ln_w, ln_b, w1, b1, w2, b2, g = _params(fp, fp=fp, d_ffn=fp)
+        x = torch.randn(777, DM, device="cuda", generator=g)
+        torch.testing.assert_close(_run(x, ln_w, ln_b, w1, b1, w2, b2),
+                                   _want(x, ln_w, ln_b, w1, b1, w2, b2), rtol=6e-3, atol=6e-3)
+
+
+def test_ffn_block_rejects_other_shapes():
+    from outfitx_b200 import _lib
+    x = torch.zeros(4, 1024, device="cuda")
+    rc = _lib.lib().ofx_ffn_block_bf16(x.data_ptr(), 4, 1024, 2048, x.data_ptr(), x.data_ptr(), x.data_ptr(),
+                                       x.data_ptr(), x.data_ptr(), x.data_ptr(), None)
+    assert rc == -1
