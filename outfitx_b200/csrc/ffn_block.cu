@@ -28,6 +28,7 @@
 // allocator, 4-11 epilogue (mish chunks, then the residual epilogue), 12-15 LayerNorm prologue
 // (x rows -> H in the swizzled K-major operand layout).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "encoder_ops.h"
 #include "ptx.cuh"
@@ -44,8 +45,9 @@ constexpr int TILE = 2 * ROWS;        // token rows per CTA pair
 constexpr int KBLK_BYTES = ROWS * 128;        // one 64-row x 64-element bf16 operand block
 constexpr int H_BYTES = KB1 * KBLK_BYTES;     // 64 KB
 constexpr int U_BYTES = KB2 * KBLK_BYTES;     // 32 KB
-constexpr int STAGE_BYTES = 128 * 128;        // 128 weight rows x 64 K per CTA per stage
-constexpr int NSTAGE = 6;
+constexpr int SUB_BYTES = 128 * 128;          // one weight sub-tile: 128 rows x 64 K per CTA
+constexpr int STAGE_BYTES = 2 * SUB_BYTES;    // ring stage = two sub-tiles = 8 MMAs per barrier wait
+constexpr int NSTAGE = 3;
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = 1024 + H_BYTES + 2 * U_BYTES + NSTAGE * STAGE_BYTES + BAR_BYTES;
 constexpr int NTHREADS = 512;
@@ -61,6 +63,8 @@ struct Params {
     const float* b1;        // (n_chunks * 256) fp32, zero beyond d_ffn
     const float* b2;        // (512)
     int n_chunks;           // padded d_ffn / 256
+    int debug;              // OFX_FFN_DEBUG: 1 = skip mish (timing experiments only)
+    long long* prof;        // debug bit 3: per-pair cycle counters of the MMA warp (8 per pair)
 };
 
 __device__ __forceinline__ float mish_fast(float x) {
@@ -143,19 +147,22 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             const int r128 = static_cast<int>(rank) * 128;
-            auto put = [&](const CUtensorMap* tm, int c_inner, int c_outer) {
+            // one ring stage = two 128-row x 64-K sub-tiles
+            auto put2 = [&](const CUtensorMap* tm, int i0, int o0, int i1, int o1) {
                 mbar_wait(&w_empty[stage], phase ^ 1);
-                if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
-                tma_load_2d_pair(s_w + stage * STAGE_BYTES, tm, mapa_shared(smem_u32(&w_full[stage]), 0),
-                                 c_inner, c_outer, kEvictLast);
+                if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);   // both CTAs' bytes
+                const uint32_t bar = mapa_shared(smem_u32(&w_full[stage]), 0);
+                tma_load_2d_pair(s_w + stage * STAGE_BYTES, tm, bar, i0, o0, kEvictLast);
+                tma_load_2d_pair(s_w + stage * STAGE_BYTES + SUB_BYTES, tm, bar, i1, o1, kEvictLast);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             };
-            auto g1 = [&](int c) {
-                for (int kb = 0; kb < KB1; ++kb) put(&tm_w1, kb * 64, c * CH + r128);
+            auto g1 = [&](int c) {   // W1 rows of chunk c, k-blocks (2j, 2j+1)
+                for (int j = 0; j < KB1 / 2; ++j)
+                    put2(&tm_w1, (2 * j) * 64, c * CH + r128, (2 * j + 1) * 64, c * CH + r128);
             };
-            auto g2 = [&](int c) {
+            auto g2 = [&](int c) {   // W2 columns of chunk c, k-block kb, output halves 0 / 1
                 for (int kb = 0; kb < KB2; ++kb)
-                    for (int half = 0; half < 2; ++half) put(&tm_w2, c * CH + kb * 64, half * 256 + r128);
+                    put2(&tm_w2, c * CH + kb * 64, r128, c * CH + kb * 64, 256 + r128);
             };
             for (int t = pair; t < n_tiles; t += n_pairs) {
                 g1(0);
@@ -170,8 +177,11 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         // ------------------------------------------------------------ MMA issuer (leader only)
         // The whole warp runs the loop (warp-uniform control flow and addresses, so the
         // descriptors live in uniform registers); one elected lane issues the tcgen05 ops.
-        // An M=128 / N=256 pair MMA occupies the tensor pipe for only 64 cycles, so the issue
-        // path has to stay within a handful of instructions per MMA.
+        // Measured: a UTCHMMA blocks its issuer until the tensor pipe accepts it (the queue is
+        // about one deep), and an M=128 / N=256 pair MMA runs for only 64 cycles, so whatever the
+        // issuing thread does between MMAs is tensor-pipe idle time.  Hence 8 MMAs per ring
+        // stage, and the mbarrier poll for the NEXT stage is issued before this stage's MMAs so
+        // that its ~100-cycle latency overlaps them.
         if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
             constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SW128
@@ -181,21 +191,36 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
             auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
             int stage = 0;
             uint32_t phase = 0, tphase = 0, uph0 = 0, uph1 = 0;
+            uint32_t ready = 0;     // result of the early poll of w_full[stage]
+            long long t_w = 0, t_u = 0, t_h = 0, t_a2 = 0, t0 = clock64(), tq;
+#define PROF_WAIT(acc, stmt) do { if (p.prof) { tq = clock64(); stmt; acc += clock64() - tq; } else { stmt; } } while (0)
+            // waits for ring stage `stage`, polls the next one, returns this stage's B descriptor base
+            auto acquire = [&](int& ns, uint32_t& nph, uint32_t& nready) -> uint32_t {
+                if (!ready) PROF_WAIT(t_w, mbar_wait(&w_full[stage], phase));
+                tc_fence_after();
+                ns = stage + 1; nph = phase;
+                if (ns == NSTAGE) { ns = 0; nph ^= 1; }
+                nready = mbar_try_wait(&w_full[ns], nph) ? 1u : 0u;
+                return w_lo + stage * (STAGE_BYTES >> 4);
+            };
             auto g1 = [&](int c) {
                 const uint32_t d = tmem_base + TM_ACC1 + (c & 1) * 128;
-                for (int kb = 0; kb < KB1; ++kb) {
-                    mbar_wait(&w_full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a = h_lo + kb * (KBLK_BYTES >> 4);
-                    const uint32_t b = w_lo + stage * (STAGE_BYTES >> 4);
+                for (int j = 0; j < KB1 / 2; ++j) {
+                    int ns; uint32_t nph, nready;
+                    const uint32_t b = acquire(ns, nph, nready);
+                    const uint32_t a = h_lo + (2 * j) * (KBLK_BYTES >> 4);
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16_pair(d, desc(a + 2 * k), desc(b + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_pair(d, desc(a + sub * (KBLK_BYTES >> 4) + 2 * k),
+                                               desc(b + sub * (SUB_BYTES >> 4) + 2 * k), idesc,
+                                               (j | sub | k) != 0 ? 1u : 0u);
                         umma_commit_pair(&w_empty[stage], 0b11);
                     }
                     __syncwarp();
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    stage = ns; phase = nph; ready = nready;
                 }
                 if (elect_one()) {
                     umma_commit_pair(&acc1_full[c & 1], 0b11);
@@ -204,37 +229,36 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 __syncwarp();
             };
             auto g2 = [&](int c) {
-                if (c & 1) { mbar_wait_cluster(&u_full[1], uph1); uph1 ^= 1; }
-                else       { mbar_wait_cluster(&u_full[0], uph0); uph0 ^= 1; }
+                if (c & 1) { PROF_WAIT(t_u, mbar_wait(&u_full[1], uph1)); uph1 ^= 1; }
+                else       { PROF_WAIT(t_u, mbar_wait(&u_full[0], uph0)); uph0 ^= 1; }
                 tc_fence_after();
                 const uint32_t ub = u_lo + (c & 1) * (U_BYTES >> 4);
                 for (int kb = 0; kb < KB2; ++kb) {
+                    int ns; uint32_t nph, nready;
+                    const uint32_t b = acquire(ns, nph, nready);
+                    const uint32_t a = ub + kb * (KBLK_BYTES >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        mbar_wait(&w_full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a = ub + kb * (KBLK_BYTES >> 4);
-                        const uint32_t b = w_lo + stage * (STAGE_BYTES >> 4);
-                        const uint32_t d = tmem_base + TM_ACC2 + half * 128;
-                        if (elect_one()) {
+                        for (int half = 0; half < 2; ++half)
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_bf16_pair(d, desc(a + 2 * k), desc(b + 2 * k), idesc, (c | kb | k) != 0 ? 1u : 0u);
-                            umma_commit_pair(&w_empty[stage], 0b11);
-                        }
-                        __syncwarp();
-                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                                umma_bf16_pair(tmem_base + TM_ACC2 + half * 128, desc(a + 2 * k),
+                                               desc(b + half * (SUB_BYTES >> 4) + 2 * k), idesc,
+                                               (c | kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair(&w_empty[stage], 0b11);
                     }
+                    __syncwarp();
+                    stage = ns; phase = nph; ready = nready;
                 }
             };
             for (int t = pair; t < n_tiles; t += n_pairs) {
-                mbar_wait_cluster(h_full, tphase);
+                PROF_WAIT(t_h, mbar_wait(h_full, tphase));
                 tc_fence_after();
                 g1(0);
                 if (nch > 1) g1(1);
                 for (int c = 0; c < nch; ++c) {
                     if (c == 0) {   // the previous tile's output has left TMEM
-                        mbar_wait_cluster(acc2_empty, tphase ^ 1);
+                        PROF_WAIT(t_a2, mbar_wait(acc2_empty, tphase ^ 1));
                         tc_fence_after();
                     }
                     g2(c);
@@ -244,6 +268,11 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 __syncwarp();
                 tphase ^= 1;
             }
+            if (p.prof && lane == 0) {
+                long long* o = p.prof + pair * 8;
+                o[0] = clock64() - t0; o[1] = t_w; o[2] = t_u; o[3] = t_h; o[4] = t_a2;
+            }
+#undef PROF_WAIT
         }
     } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + N_EPI_WARPS) {
         // ------------------------------------------------------------ epilogue warps
@@ -284,10 +313,11 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const float4 bb = bv[2 * j + h];
-                            const float v0 = mish_fast(__uint_as_float(raw[8 * j + 4 * h + 0]) + bb.x);
-                            const float v1 = mish_fast(__uint_as_float(raw[8 * j + 4 * h + 1]) + bb.y);
-                            const float v2 = mish_fast(__uint_as_float(raw[8 * j + 4 * h + 2]) + bb.z);
-                            const float v3 = mish_fast(__uint_as_float(raw[8 * j + 4 * h + 3]) + bb.w);
+                            float v0 = __uint_as_float(raw[8 * j + 4 * h + 0]) + bb.x;
+                            float v1 = __uint_as_float(raw[8 * j + 4 * h + 1]) + bb.y;
+                            float v2 = __uint_as_float(raw[8 * j + 4 * h + 2]) + bb.z;
+                            float v3 = __uint_as_float(raw[8 * j + 4 * h + 3]) + bb.w;
+                            if (!(p.debug & 1)) { v0 = mish_fast(v0); v1 = mish_fast(v1); v2 = mish_fast(v2); v3 = mish_fast(v3); }
                             w[2 * h] = pack_bf16(v0, v1);
                             w[2 * h + 1] = pack_bf16(v2, v3);
                         }
@@ -346,9 +376,16 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         const uint32_t hfull = mapa_shared(smem_u32(h_full), 0);
         uint32_t tphase = 0;
         for (int t = pair; t < n_tiles; t += n_pairs) {
+            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 16;
+            // pull this warp's 16 rows (32 KB) towards L2 while the previous tile still owns H
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long off = (row0 * DM + (i * 32 + lane) * 32) ;   // 128-byte lines
+                if (row0 + (i * 32 + lane) / 16 < n_rows)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + off));
+            }
             mbar_wait(h_empty, tphase ^ 1);     // GEMM 1 of the previous tile has consumed H
             tphase ^= 1;
-            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 16;
 #pragma unroll 1
             for (int rb = 0; rb < 16; rb += 4) {
                 float4 v[4][4];
@@ -417,6 +454,8 @@ int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
     if (a.dm != DM || a.fp <= 0 || a.fp % CH != 0)
         return fail(OFX_E_SHAPE, "ffn_block: needs d_model 512 and padded d_ffn %% 256 == 0 (got %d, %d)", a.dm, a.fp);
     CUtensorMap tm_w1, tm_w2;
+    static int debug = -1;
+    if (debug < 0) { const char* e = getenv("OFX_FFN_DEBUG"); debug = e ? atoi(e) : 0; }
     OFX_TRY(make_tmap_bf16(&tm_w1, a.w1, static_cast<uint64_t>(a.fp), DM, DM, 128));
     OFX_TRY(make_tmap_bf16(&tm_w2, a.w2, DM, static_cast<uint64_t>(a.fp), a.fp, 128));
     static bool configured = false;
@@ -427,9 +466,25 @@ int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
     const int n_tiles = (a.rows + TILE - 1) / TILE;
     const int max_pairs = sm_count() / 2;
     const int pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    Params p{a.x, a.rows, a.rows_dev, a.ln_w, a.ln_b, a.b1, a.b2, a.fp / CH};
+    Params p{a.x, a.rows, a.rows_dev, a.ln_w, a.ln_b, a.b1, a.b2, a.fp / CH, debug, nullptr};
+    static long long* prof_dev = nullptr;
+    if (debug & 8) {
+        if (!prof_dev) OFX_CUDA(cudaMalloc(&prof_dev, 8 * 8 * 128));
+        OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 128, stream));
+        p.prof = prof_dev;
+    }
     ffn_block_kernel<<<pairs * 2, NTHREADS, SMEM_BYTES, stream>>>(tm_w1, tm_w2, p);
     OFX_LAUNCH_CHECK();
+    if (debug & 8) {   // debug only: synchronous dump of the MMA warp's wait-cycle counters
+        static int dumps = 0;
+        long long h[8 * 128];
+        OFX_CUDA(cudaStreamSynchronize(stream));
+        OFX_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        if (dumps++ < 2)
+            for (int i = 0; i < pairs && i < 74; i += 18)
+                fprintf(stderr, "ffn prof pair %d: total %lld  w_full %lld  u_full %lld  h_full %lld  acc2_empty %lld cycles\n",
+                        i, h[i * 8], h[i * 8 + 1], h[i * 8 + 2], h[i * 8 + 3], h[i * 8 + 4]);
+    }
     return OFX_OK;
 }
 

@@ -163,8 +163,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank
 }
 // arrive on a barrier of any CTA of the cluster (address from mapa_shared)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-                 : "memory");
+    // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id):
+    // a .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR, ~1-2k cycles per arrive.
+    // The operand data never crosses CTAs through the generic proxy here: each CTA's UMMA reads
+    // that CTA's own shared memory after the writer's fence.proxy.async.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
