@@ -5,6 +5,8 @@
 // nn.TransformerEncoderLayer (in_proj, out_proj, linear1+mish, linear2).
 #include "gemm.h"
 
+#include <stdlib.h>
+
 #include "tc_pipeline.cuh"
 
 namespace ofx {
@@ -191,7 +193,22 @@ static int launch_tc(const GemmArgs& g, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
+    static int prof_on = -1;
+    static long long* prof_dev = nullptr;
+    if (prof_on < 0) { const char* e = getenv("OFX_TC_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
+    if (prof_on) {   // debug only: synchronous dump of per-CTA wait counters
+        if (!prof_dev) OFX_CUDA(cudaMalloc(&prof_dev, 8 * 8 * 256));
+        OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 256, stream));
+        OFX_CUDA(cudaMemcpyToSymbolAsync(g_tc_prof, &prof_dev, sizeof(prof_dev), 0, cudaMemcpyHostToDevice, stream));
+    }
     OFX_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, sp, ep, g.k / kBK));
+    if (prof_on) {
+        long long h[8 * 256];
+        OFX_CUDA(cudaStreamSynchronize(stream));
+        OFX_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "tc prof M=%d N=%d K=%d BN=%d CL=%d: cta0 mma total %lld wait_full %lld wait_tmem_empty %lld | epi total %lld wait_tmem_full %lld ; cta100 mma %lld %lld %lld | epi %lld %lld\n",
+                g.m, g.n, g.k, BN, CL, h[0], h[1], h[2], h[4], h[5], h[800], h[801], h[802], h[804], h[805]);
+    }
     return OFX_OK;
 }
 

@@ -63,6 +63,10 @@ constexpr int tc_smem_bytes() {
 template <class Epi>
 constexpr int tc_threads() { return 128 + 32 * Epi::kWarps; }
 
+// Debug instrumentation (OFX_TC_PROF=1, gemm.cu): per-CTA cycle counters of the MMA warp
+// {total, wait smem-full, wait tmem-empty} and of epilogue warp 0 {total, wait tmem-full}.
+__device__ long long* g_tc_prof = nullptr;
+
 template <int BN, int STAGES, int CL, class Sched, class Epi>
 __global__ void __launch_bounds__(128 + 32 * Epi::kWarps, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -146,12 +150,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             Sched sched(sp, blockIdx.x, gridDim.x);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
+            long long* prof = g_tc_prof;
+            long long t0 = clock64(), t_full = 0, t_te = 0, tq;
             while (sched.next()) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                if (prof) { tq = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); t_te += clock64() - tq; }
+                else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    if (prof) { tq = clock64(); mbar_wait(&full[stage], phase); t_full += clock64() - tq; }
+                    else mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_lo = a_lo0 + stage * (Cfg::kABytes >> 4);
                     const uint32_t b_lo = b_lo0 + stage * (Cfg::kBBytes >> 4);
@@ -171,6 +179,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                 __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            if (prof && lane == 0) {
+                prof[blockIdx.x * 8 + 0] = clock64() - t0; prof[blockIdx.x * 8 + 1] = t_full; prof[blockIdx.x * 8 + 2] = t_te;
+            }
         }
     } else if (warp >= kEpiWarp0) {
         // ------------------------------------------------------------ epilogue
@@ -181,8 +192,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         uint32_t acc_phase = 0;
         Epi epi;
         epi.begin(ep, sched, ewarp, lane, epi_smem);
+        long long* prof = g_tc_prof;
+        long long t0 = clock64(), t_tf = 0, tq;
         while (sched.next()) {
-            mbar_wait(&tmem_full[acc], acc_phase);
+            if (prof) { tq = clock64(); mbar_wait(&tmem_full[acc], acc_phase); t_tf += clock64() - tq; }
+            else mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
             epi.tile(ep, sched, t_acc, ewarp, lane, epi_smem);
@@ -190,6 +204,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (prof && ewarp == 0 && lane == 0) {
+            prof[blockIdx.x * 8 + 4] = clock64() - t0; prof[blockIdx.x * 8 + 5] = t_tf;
         }
     }
     tc_fence_before();
