@@ -164,6 +164,8 @@ struct EpiTopK {
         cnt = 0; lpos = 0; lidx = 0; lmin = 0.f; thr = -INFINITY; full = false;
     }
 
+    __device__ void end(const Params&, int) {}
+
     // evict candidate = lowest score, highest index among equal scores.  Static + by-value so
     // the per-thread state stays in registers (no `this` escaping into local memory).
     static __device__ __noinline__ float4 find_evict(const float* ls, const int* li) {

@@ -39,7 +39,7 @@ struct TcCfg {
     static constexpr int kStages = STAGES;
     static constexpr int kTmemCols = 2 * BN;  // power of two for BN in {64,128,256}
     static constexpr int kRingBytes = kStages * kStageBytes;
-    static constexpr int kBarBytes = 256;  // barriers + tmem slot
+    static constexpr int kBarBytes = 1024;  // barriers + tmem slot; keeps the epilogue smem 1024-byte aligned (TMA swizzle)
 };
 
 template <int BN, int STAGES, class Epi>
@@ -56,6 +56,7 @@ constexpr int tc_smem_bytes() {
 //   struct Params; static constexpr int kSmemBytes;
 //   static constexpr int kWarps;   4 or 8 epilogue warps
 //   __device__ void begin(const Params&, const Sched&, int ewarp, int lane, uint8_t* smem);
+//   __device__ void end(const Params&, int lane);   after the last tile (e.g. drain bulk stores)
 //   __device__ void tile(const Params&, const Sched&, uint32_t tmem_acc /*lane quarter applied*/,
 //                        int ewarp /*0..kWarps-1: quarter = ewarp & 3, column group = ewarp >> 2*/,
 //                        int lane, uint8_t* epi_smem);
@@ -70,7 +71,8 @@ __device__ long long* g_tc_prof = nullptr;
 template <int BN, int STAGES, int CL, class Sched, class Epi>
 __global__ void __launch_bounds__(128 + 32 * Epi::kWarps, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-          const typename Sched::Params sp, const typename Epi::Params ep, const int num_k_blocks) {
+          const typename Sched::Params sp, const __grid_constant__ typename Epi::Params ep,
+          const int num_k_blocks) {
     using Cfg = TcCfg<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte aligned bases
@@ -205,6 +207,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        epi.end(ep, lane);
         if (prof && ewarp == 0 && lane == 0) {
             prof[blockIdx.x * 8 + 4] = clock64() - t0; prof[blockIdx.x * 8 + 5] = t_tf;
         }
