@@ -1,0 +1,94 @@
+"""Host-to-result scoring pipeline: the H2D boundary of the reference's callers, overlapped.
+
+The reference moves every collated batch to the GPU and then runs the model on it
+(``v.to(local_rank)`` followed by ``model(**input_dict)``,
+``src/trains/trainers/compatibility_prediction_trainer.py:140-145``; the demo does the same,
+``src/demo/app.py:124-130``), so copy and compute are serialised.  At 64 KB of fp32 embeddings
+per outfit (16 slots x (512 + 512) floats) the copy is the longer of the two on a PCIe-attached
+B200, so this module splits a host batch into chunks and double-buffers them: chunk i+1 crosses
+PCIe on a copy stream while chunk i is scored on the compute stream, and results return through
+pinned host buffers.  Everything it calls is the public ``OutfitX`` API; it adds no arithmetic.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+
+class HostScoringPipeline:
+    """Scores host-resident batches with ``model`` (an ``outfitx_b200.OutfitX`` on a CUDA device).
+
+    ``chunk``: outfits per device chunk.  Inputs should be pinned (``tensor.pin_memory()``) for
+    the copies to be asynchronous; pageable tensors work but serialise.
+    """
+
+    def __init__(self, model, chunk: int = 2048):
+        if chunk < 1:
+            raise ValueError("chunk must be >= 1")
+        self.model, self.chunk = model, chunk
+        dev = model.device
+        if dev.type != "cuda":
+            raise RuntimeError("the model must be on a CUDA device: outfitx_b200 has no CPU path")
+        self.dev = dev
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.compute_stream = torch.cuda.Stream(dev)
+        self._slots = [dict(), dict()]          # device staging buffers, two in flight
+        self._free = [torch.cuda.Event(), torch.cuda.Event()]   # slot may be overwritten
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]  # slot's copies have landed
+
+    def _stage(self, slot: int, name: str, src: torch.Tensor) -> torch.Tensor:
+        buf = self._slots[slot].get(name)
+        if buf is None or buf.shape[1:] != src.shape[1:] or buf.dtype != src.dtype or buf.shape[0] < src.shape[0]:
+            buf = torch.empty((self.chunk,) + tuple(src.shape[1:]), dtype=src.dtype, device=self.dev)
+            self._slots[slot][name] = buf
+        view = buf[: src.shape[0]]
+        view.copy_(src, non_blocking=True)
+        return view
+
+    @torch.no_grad()
+    def score(self, image_embeddings: torch.Tensor, text_embeddings: torch.Tensor, outfit_mask: torch.Tensor,
+              target_item_text_embedding: Optional[torch.Tensor] = None,
+              candidate_item_embedding: Optional[torch.Tensor] = None,
+              out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """CP probabilities (and, when ``target_item_text_embedding`` + ``candidate_item_embedding``
+        are given, FITB predictions) for a HOST batch of raw per-modality embeddings
+        ``(B, L, dim_per_modality)``.  Returns pinned host tensors ``probs (B,)`` [, ``pred (B,)``];
+        the call returns once they are valid."""
+        B = image_embeddings.shape[0]
+        fitb = candidate_item_embedding is not None
+        if fitb and target_item_text_embedding is None:
+            raise ValueError("FITB scoring needs target_item_text_embedding")
+        if out is None:
+            out = {"probs": torch.empty(B, dtype=torch.float32).pin_memory()}
+            if fitb:
+                out["pred"] = torch.empty(B, dtype=torch.int64).pin_memory()
+        cur = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(cur)
+        self.compute_stream.wait_stream(cur)
+        for i, lo in enumerate(range(0, B, self.chunk)):
+            hi = min(B, lo + self.chunk)
+            s = i & 1
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(self._free[s])
+                d = {"img": self._stage(s, "img", image_embeddings[lo:hi]),
+                     "txt": self._stage(s, "txt", text_embeddings[lo:hi]),
+                     "mask": self._stage(s, "mask", outfit_mask[lo:hi])}
+                if fitb:
+                    d["text"] = self._stage(s, "text", target_item_text_embedding[lo:hi])
+                    d["cand"] = self._stage(s, "cand", candidate_item_embedding[lo:hi])
+                self._ready[s].record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(self._ready[s])
+                enc = {"image_embeddings": d["img"], "text_embeddings": d["txt"]}
+                probs = self.model.score_cp(outfit_mask=d["mask"], encoder_input_dict=enc)
+                out["probs"][lo:hi].copy_(probs, non_blocking=True)
+                if fitb:
+                    pred, _, _ = self.model.score_fitb(outfit_mask=d["mask"], target_item_text_embedding=d["text"],
+                                                       candidate_item_embedding=d["cand"], encoder_input_dict=enc)
+                    out["pred"][lo:hi].copy_(pred, non_blocking=True)
+                self._free[s].record(self.compute_stream)
+        cur.wait_stream(self.compute_stream)
+        self.compute_stream.synchronize()
+        return out
