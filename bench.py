@@ -28,6 +28,11 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: everything libraries print to fd 1 (e.g. NCCL's version
+# banner) is sent to stderr instead, and the result line goes to the saved descriptor.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 from outfitx_b200 import synth  # noqa: E402
 
 D_MODEL, D_EMBED, DPM, F_FFN, N_LAYERS = 512, 1024, 512, 2024, 6
@@ -282,7 +287,7 @@ def run_reference(args, rank, world):
                 "sample": "topk(cdist) on 256 q x 200k items, scaled linearly in nq*N"},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def main():
@@ -317,6 +322,7 @@ def main():
     dist_ok = world > 1
     if dist_ok:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     pk = peaks()
@@ -456,7 +462,7 @@ def main():
             "cpu_baseline": cpu,
             "cir": cir,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if dist_ok:
         dist.barrier()
         dist.destroy_process_group()

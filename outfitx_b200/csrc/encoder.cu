@@ -170,7 +170,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
         const bool last = l == L.nl - 1;
         if (l > 0) OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln1w), lf(l, L.ln1b), h, st));
         AttnArgs at{};
-        at.batch = B; at.n_head = s->n_head; at.off = off;
+        at.batch = B; at.n_head = s->n_head; at.off = off; at.max_s = s->max_items + 1;
         at.max_rows = W.t_max; at.n_tok = n_tok; at.owner = owner;
         if (!last) {
             // dense layer over every valid token

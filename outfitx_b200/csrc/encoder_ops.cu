@@ -483,14 +483,16 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
 
 constexpr int kAttnMaxS = 17;
 
-template <int HD>
-__global__ void __launch_bounds__(128)
-attention_mma_kernel(AttnArgs a) {
+// BIG = false: this outfit has S <= 16 tokens (one 16-row query tile, one 16-key tile) -- 14 of 15
+// outfits when n ~ U{2..16}; BIG = true adds the second tiles for S = 17.  The kernel picks the
+// body per CTA, so the common case runs straight-line code without per-tile predicates.
+template <int HD, bool BIG>
+__device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* sm) {
+    constexpr int MT = BIG ? 2 : 1, KT = BIG ? 2 : 1;
     constexpr int DM = 16 * HD;
     constexpr int CPR = DM / 8;              // 16-byte chunks per row
     constexpr int STRIDE = (DM + 8) * 2;     // bytes per shared-memory row
     constexpr int KS = HD / 16;              // k-steps over the head dimension
-    extern __shared__ __align__(16) uint8_t sm[];
     uint8_t* s_q = sm;
     uint8_t* s_k = sm + kAttnMaxS * STRIDE;
     uint8_t* s_v = s_k + kAttnMaxS * STRIDE;
@@ -527,8 +529,8 @@ attention_mma_kernel(AttnArgs a) {
     const uint32_t k_s = static_cast<uint32_t>(__cvta_generic_to_shared(s_k));
     const uint32_t v_s = static_cast<uint32_t>(__cvta_generic_to_shared(s_v));
     const uint32_t z_s = static_cast<uint32_t>(__cvta_generic_to_shared(s_z));
-    const int n_mt = n_q > 16 ? 2 : 1;     // 16-row query tiles
-    const int n_kt = S > 16 ? 2 : 1;       // 16-key tiles
+    const int n_mt = BIG && n_q > 16 ? 2 : 1;     // 16-row query tiles in use
+    const int n_kt = BIG && S > 16 ? 2 : 1;       // 16-key tiles in use
     const int g = lane >> 2, t4 = lane & 3;
     // ldmatrix row / column roles of this lane
     const int a_row = (lane & 7) + 8 * ((lane >> 3) & 1), a_col = 8 * (lane >> 4);     // A operand (q) and V^T
@@ -538,31 +540,31 @@ attention_mma_kernel(AttnArgs a) {
 #pragma unroll 1
     for (int hh = 0; hh < 4; ++hh) {
         const int col0 = (warp * 4 + hh) * HD;     // first column of this head
-        float sc[2][4][4];                          // [query tile][8-key tile][fragment]
+        float sc[MT][2 * KT][4];                          // [query tile][8-key tile][fragment]
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < 2 * KT; ++nt)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) sc[mt][nt][e] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-            uint32_t qa[2][4];
+            uint32_t qa[MT][4];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 if (mt < n_mt) {
                     const int r = mt * 16 + a_row;
                     ldsm_x4(qa[mt], (r < n_q ? q_s + r * STRIDE : z_s) + (col0 + ks * 16 + a_col) * 2);
                 }
             }
 #pragma unroll
-            for (int kt = 0; kt < 2; ++kt) {
+            for (int kt = 0; kt < KT; ++kt) {
                 if (kt < n_kt) {
                     uint32_t kb[4];
                     const int r = kt * 16 + b_row;
                     ldsm_x4(kb, (r < S ? k_s + r * STRIDE : z_s) + (col0 + ks * 16 + b_col) * 2);
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
+                    for (int mt = 0; mt < MT; ++mt) {
                         if (mt < n_mt) {
                             mma_bf16_16816(sc[mt][2 * kt], qa[mt], kb[0], kb[1]);
                             mma_bf16_16816(sc[mt][2 * kt + 1], qa[mt], kb[2], kb[3]);
@@ -572,16 +574,16 @@ attention_mma_kernel(AttnArgs a) {
             }
         }
         // masked softmax over the keys of each query row (rows g and g + 8 of every tile)
-        uint32_t pa[2][2][4];      // P as the A operand of P.V: [query tile][16-key tile]
-        float inv[2][2];
+        uint32_t pa[MT][KT][4];      // P as the A operand of P.V: [query tile][16-key tile]
+        float inv[MT][2];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < MT; ++mt) {
             if (mt < n_mt) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {       // h = 0: row g, h = 1: row g + 8
                     float mx = -INFINITY;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
+                    for (int nt = 0; nt < 2 * KT; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int key = nt * 8 + 2 * t4 + e;
@@ -593,7 +595,7 @@ attention_mma_kernel(AttnArgs a) {
                     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
                     float sum = 0.f;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
+                    for (int nt = 0; nt < 2 * KT; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const float pz = ex2_fast(sc[mt][nt][2 * h + e] - mx);   // key 0 is always valid: mx finite
@@ -605,7 +607,7 @@ attention_mma_kernel(AttnArgs a) {
                     inv[mt][h] = 1.f / sum;
                 }
 #pragma unroll
-                for (int kt = 0; kt < 2; ++kt) {
+                for (int kt = 0; kt < KT; ++kt) {
                     pa[mt][kt][0] = pack2_bf16(sc[mt][2 * kt][0], sc[mt][2 * kt][1]);
                     pa[mt][kt][1] = pack2_bf16(sc[mt][2 * kt][2], sc[mt][2 * kt][3]);
                     pa[mt][kt][2] = pack2_bf16(sc[mt][2 * kt + 1][0], sc[mt][2 * kt + 1][1]);
@@ -616,21 +618,21 @@ attention_mma_kernel(AttnArgs a) {
         // out = P . V, 16 head dims at a time
 #pragma unroll
         for (int dp = 0; dp < KS; ++dp) {
-            float o[2][2][4];
+            float o[MT][2][4];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                 for (int x = 0; x < 2; ++x)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o[mt][x][e] = 0.f;
 #pragma unroll
-            for (int kt = 0; kt < 2; ++kt) {
+            for (int kt = 0; kt < KT; ++kt) {
                 if (kt < n_kt) {
                     uint32_t vb[4];
                     const int r = kt * 16 + a_row;
                     ldsm_x4_trans(vb, (r < S ? v_s + r * STRIDE : z_s) + (col0 + dp * 16 + a_col) * 2);
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
+                    for (int mt = 0; mt < MT; ++mt) {
                         if (mt < n_mt) {
                             mma_bf16_16816(o[mt][0], pa[mt][kt], vb[0], vb[1]);
                             mma_bf16_16816(o[mt][1], pa[mt][kt], vb[2], vb[3]);
@@ -641,7 +643,7 @@ attention_mma_kernel(AttnArgs a) {
             // the head's slice of the q rows is dead (fragments are in registers): reuse it for the output
             __syncwarp();
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
                 if (mt < n_mt) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -664,6 +666,15 @@ attention_mma_kernel(AttnArgs a) {
         const long long row = r == 0 ? b : base + r - 1;
         *reinterpret_cast<uint4*>(go + row * a.ldo + cc * 8) = *reinterpret_cast<const uint4*>(s_q + r * STRIDE + cc * 16);
     }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const AttnArgs a) {
+    extern __shared__ __align__(16) uint8_t attn_sm[];
+    const int b = blockIdx.x;
+    if (a.off[b + 1] - a.off[b] < 16) attention_mma_body<HD, false>(a, attn_sm);   // S = 1 + n <= 16
+    else attention_mma_body<HD, true>(a, attn_sm);
 }
 
 template <int HD>

@@ -21,6 +21,7 @@ struct AssembleArgs {
 
 struct AttnArgs {
     int batch, n_head, row0_only;
+    int max_s;             // upper bound of tokens per outfit (1 + max_items)
     int max_rows;          // host upper bound of token rows
     const int* n_tok;      // device token-row count
     const int* owner;      // token row -> outfit (rows >= batch)

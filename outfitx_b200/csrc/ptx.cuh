@@ -100,6 +100,36 @@ constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 
+// ---------------------------------------------------------------- explicit address spaces
+// Pointers derived from the realigned dynamic-smem base (an integer round trip) or read from
+// by-value parameter structs reach ptxas as GENERIC pointers: it then emits LD.E / ST.E, and --
+// worse -- cannot reorder a "maybe shared" access against a "maybe global" one, so load batches
+// get serialised behind stores.  The hot paths therefore name the state space.
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 ldg128(const float* p) {      // coherent global load
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg128_nc(const float* p) {   // read-only path (data not written by this kernel's other threads)
+    float4 v;
+    asm("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg128(float* p, float4 v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA store (smem -> global)
 // 2D tile store: the box described by `tmap` is read from shared memory (128B-swizzled rows)
 // and written to global memory; rows / columns outside the tensor are clipped by the hardware.

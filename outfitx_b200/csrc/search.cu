@@ -211,32 +211,45 @@ struct EpiTopK {
             thr = live ? dec_score(__ldcg(p.thr_enc + row)) : INFINITY;
         }
         const long long col_lim = p.n_rows - s.n0;  // columns >= col_lim are padding
+        // -0.5|g|^2 of this lane's column in each of the 8 slabs, fetched up front: one exposed
+        // global-load latency per tile instead of one per slab (the epilogue warps have no other
+        // warp on their SMSP to hide it behind, and with ~220 KB of shared memory there is no L1)
+        float hq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            hq[j] = (p.half_sqnorm && j * 32 + lane < col_lim) ? -__ldg(p.half_sqnorm + s.n0 + j * 32 + lane) : 0.f;
 #pragma unroll 1
         for (int c = 0; c < kSearchBN; c += 32) {
             uint32_t raw[32];
             tmem_ld_32x32(t_acc + c, raw);
-            float hb = 0.f;
-            if (p.half_sqnorm && c + lane < col_lim) hb = -__ldg(p.half_sqnorm + s.n0 + c + lane);
+            const float hb = hq[0];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) hq[j] = hq[j + 1];   // rotate: the loop stays rolled, hq stays in registers
             tmem_ld_wait();
             float v[32];
-            float mx = -INFINITY;
             if (p.half_sqnorm) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = __uint_as_float(raw[i]) + __shfl_sync(0xffffffffu, hb, i);
-                    mx = fmaxf(mx, v[i]);
-                }
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + __shfl_sync(0xffffffffu, hb, i);
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = __uint_as_float(raw[i]);
-                    mx = fmaxf(mx, v[i]);
-                }
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
             }
-            if (mx >= thr) {  // rare once the threshold has warmed up
+            float m4[4] = {v[0], v[1], v[2], v[3]};      // four independent max chains instead of one
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (v[i] >= thr && c + i < col_lim) insert(v[i], s.n0 + c + i);
+            for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            if (mx >= thr) {
+                // Taken by the whole warp as soon as ONE of its 32 queries has a candidate in this
+                // slab (about half of all slabs over a sweep), so the path must be short: the four
+                // strided partial maxima say which 8 columns can hold candidates.
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    if (m4[qd] >= thr) {
+#pragma unroll
+                        for (int i = qd; i < 32; i += 4) {
+                            if (v[i] >= thr && c + i < col_lim) insert(v[i], s.n0 + c + i);
+                        }
+                    }
                 }
             }
         }
@@ -499,7 +512,22 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
+    static int prof_on = -1;
+    static long long* prof_dev = nullptr;
+    if (prof_on < 0) { const char* e = getenv("OFX_TC_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
+    if (prof_on) {   // debug only: synchronous dump of per-CTA wait counters (tc_pipeline.cuh)
+        if (!prof_dev) OFX_CUDA(cudaMalloc(&prof_dev, 8 * 8 * 256));
+        OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 256, stream));
+        OFX_CUDA(cudaMemcpyToSymbolAsync(g_tc_prof, &prof_dev, sizeof(prof_dev), 0, cudaMemcpyHostToDevice, stream));
+    }
     OFX_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_q, tm_g, sp, ep, dim / kBK));
+    if (prof_on) {
+        long long h[8 * 256];
+        OFX_CUDA(cudaStreamSynchronize(stream));
+        OFX_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "search prof nq=%d rows=%lld grid=%d cl=%d seg_tiles=%d sub=%d: cta0 mma total %lld wait_full %lld wait_tmem_empty %lld | epi total %lld wait_tmem_full %lld ; cta100 mma %lld %lld %lld | epi %lld %lld\n",
+                n_query, n_rows, pl.grid, CL, pl.seg_tiles, pl.sub_tiles, h[0], h[1], h[2], h[4], h[5], h[800], h[801], h[802], h[804], h[805]);
+    }
     return OFX_OK;
 }
 
