@@ -149,7 +149,8 @@ OFX_API int ofx_encoder_forward(const ofx_shape* shape, const void* packed_weigh
  * arg-max of  q.g - 0.5|g|^2  (OFX_METRIC_L2, same ranking as ascending L2 distance) or of
  * q.g (OFX_METRIC_DOT); ties are broken by the lowest gallery index. */
 OFX_API size_t ofx_gallery_packed_bytes(int64_t n_rows, int32_t dim);
-/* gallery (n_rows, dim) fp32 -> packed bf16 rows + fp32 0.5|g|^2 (computed from the fp32 data) */
+/* gallery (n_rows, dim) fp32 -> packed bf16 rows of dim + 64 columns (the extra k-block carries
+ * -0.5|g|^2 as bf16 hi + lo, so the L2 bias is part of the contraction) + fp32 0.5|g|^2 */
 OFX_API int ofx_gallery_pack(const float* gallery, int64_t n_rows, int32_t dim, void* packed,
                      void* stream);
 OFX_API size_t ofx_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_query, int32_t k);

@@ -22,6 +22,13 @@ namespace ofx {
 
 constexpr int kSearchBN = 256;
 constexpr int kMaxSegments = 64;
+// The L2 metric's per-row bias -0.5|g|^2 rides in the contraction itself: every packed gallery
+// row carries one extra k-block of 64 bf16 whose first two entries are the bias split into
+// bf16 hi + lo parts (16 mantissa bits, error ~1e-5 against ~1e-3 of bf16 score noise), and the
+// bf16 copy of a query carries 1, 1 there (0, 0 for the dot metric).  One more k-block in 17
+// (+6 % tensor work) removes the bias add -- 64 of the ~100 epilogue instructions per 32-column
+// slab (32 shuffles + 32 adds) -- from an epilogue that was the kernel's bottleneck.
+constexpr int kAugCols = 64;
 
 // order-preserving float <-> uint32 map (for atomicMax on scores); 0 is below every float
 __device__ __forceinline__ uint32_t enc_score(float f) {
@@ -140,7 +147,6 @@ static SearchPlan make_plan(long long n_rows, int n_query, int n_sm) {
 template <int KCAP>
 struct EpiTopK {
     struct Params {
-        const float* half_sqnorm;  // (n_rows) 0.5|g|^2, or nullptr for the dot metric
         long long n_rows;
         int n_query;
         uint32_t* thr_enc;         // (n_qblocks * 128) encoded per-query thresholds
@@ -211,29 +217,14 @@ struct EpiTopK {
             thr = live ? dec_score(__ldcg(p.thr_enc + row)) : INFINITY;
         }
         const long long col_lim = p.n_rows - s.n0;  // columns >= col_lim are padding
-        // -0.5|g|^2 of this lane's column in each of the 8 slabs, fetched up front: one exposed
-        // global-load latency per tile instead of one per slab (the epilogue warps have no other
-        // warp on their SMSP to hide it behind, and with ~220 KB of shared memory there is no L1)
-        float hq[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            hq[j] = (p.half_sqnorm && j * 32 + lane < col_lim) ? -__ldg(p.half_sqnorm + s.n0 + j * 32 + lane) : 0.f;
 #pragma unroll 1
         for (int c = 0; c < kSearchBN; c += 32) {
             uint32_t raw[32];
             tmem_ld_32x32(t_acc + c, raw);
-            const float hb = hq[0];
-#pragma unroll
-            for (int j = 0; j < 7; ++j) hq[j] = hq[j + 1];   // rotate: the loop stays rolled, hq stays in registers
             tmem_ld_wait();
-            float v[32];
-            if (p.half_sqnorm) {
+            float v[32];     // scores; the L2 bias is already inside (augmented k-block, see kAugCols)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + __shfl_sync(0xffffffffu, hb, i);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-            }
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
             float m4[4] = {v[0], v[1], v[2], v[3]};      // four independent max chains instead of one
 #pragma unroll
             for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
@@ -269,11 +260,16 @@ struct EpiTopK {
 // ---------------------------------------------------------------------------------------
 // fp32 -> bf16 rows (queries), and gallery packing (bf16 rows + 0.5|g|^2 from the fp32 data)
 // ---------------------------------------------------------------------------------------
+// queries (nq, dim) fp32 -> (nq, dim + kAugCols) bf16 with the bias selector columns
 __global__ void __launch_bounds__(256)
-to_bf16_kernel(const float* __restrict__ in, long long n, __nv_bfloat16* __restrict__ out) {
+to_bf16_kernel(const float* __restrict__ in, int n_query, int dim, float aug, __nv_bfloat16* __restrict__ out) {
+    const int pitch = dim + kAugCols;
     const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4;
-    if (i >= n) return;
-    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    if (i >= static_cast<long long>(n_query) * pitch) return;
+    const int row = static_cast<int>(i / pitch), col = static_cast<int>(i - static_cast<long long>(row) * pitch);
+    float4 v;
+    if (col < dim) v = *reinterpret_cast<const float4*>(in + static_cast<long long>(row) * dim + col);
+    else v = col == dim ? make_float4(aug, aug, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&a);
@@ -287,6 +283,7 @@ gallery_pack_kernel(const float* __restrict__ g, long long n_rows, int dim,
     const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const int lane = threadIdx.x & 31;
+    const int pitch = dim + kAugCols;
     float ss = 0.f;
     for (int e = lane * 4; e < dim; e += 128) {
         const float4 v = *reinterpret_cast<const float4*>(g + row * dim + e);
@@ -295,11 +292,19 @@ gallery_pack_kernel(const float* __restrict__ g, long long n_rows, int dim,
         uint2 u;
         u.x = *reinterpret_cast<uint32_t*>(&a);
         u.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(out + row * dim + e) = u;
+        *reinterpret_cast<uint2*>(out + row * pitch + e) = u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if (lane == 0) half_sqnorm[row] = 0.5f * ss;
+    // bias columns: -0.5|g|^2 = hi + lo in bf16, then zeros (2 x 4 bytes per lane = 64 columns)
+    const float bias = -0.5f * ss;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(bias);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(bias - __bfloat162float(hi));
+    __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f), first;
+    first.x = hi; first.y = lo;
+    __nv_bfloat162* aug = reinterpret_cast<__nv_bfloat162*>(out + row * pitch + dim);
+    aug[lane] = lane == 0 ? first : z;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -455,7 +460,7 @@ struct PackedGallery {
 };
 static PackedGallery gallery_layout(long long n_rows, int dim) {
     PackedGallery g{};
-    g.rows_bytes = align_up(static_cast<size_t>(n_rows) * dim * 2, 256);
+    g.rows_bytes = align_up(static_cast<size_t>(n_rows) * (dim + kAugCols) * 2, 256);
     g.total = g.rows_bytes + align_up(static_cast<size_t>(n_rows) * 4, 256);
     return g;
 }
@@ -474,7 +479,7 @@ static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     const size_t slots = static_cast<size_t>(w.plan.n_units) * w.plan.cl * 128;
-    w.q_bf16 = take(static_cast<size_t>(n_query) * dim * 2);
+    w.q_bf16 = take(static_cast<size_t>(n_query) * (dim + kAugCols) * 2);
     w.thr = take(static_cast<size_t>(w.plan.n_qgroups) * w.plan.cl * 128 * 4);
     w.cand_n = take(slots * 4);
     w.cand_s = take(slots * w.kcap * 4);
@@ -489,8 +494,9 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
                          cudaStream_t stream) {
     using Epi = EpiTopK<KCAP>;
     CUtensorMap tm_q, tm_g;
-    OFX_TRY(make_tmap_bf16(&tm_q, q_bf16, static_cast<uint64_t>(n_query), dim, dim, kBM));
-    OFX_TRY(make_tmap_bf16(&tm_g, gallery, static_cast<uint64_t>(n_rows), dim, dim, kSearchBN / CL));
+    const int kdim = dim + kAugCols;   // contraction length including the bias k-block
+    OFX_TRY(make_tmap_bf16(&tm_q, q_bf16, static_cast<uint64_t>(n_query), kdim, kdim, kBM));
+    OFX_TRY(make_tmap_bf16(&tm_g, gallery, static_cast<uint64_t>(n_rows), kdim, kdim, kSearchBN / CL));
     auto kern = tc_kernel<kSearchBN, STAGES, CL, SchedSearch, Epi>;
     constexpr int smem = tc_smem_bytes<kSearchBN, STAGES, Epi>();
     static bool configured = false;
@@ -520,7 +526,7 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
         OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 256, stream));
         OFX_CUDA(cudaMemcpyToSymbolAsync(g_tc_prof, &prof_dev, sizeof(prof_dev), 0, cudaMemcpyHostToDevice, stream));
     }
-    OFX_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_q, tm_g, sp, ep, dim / kBK));
+    OFX_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_q, tm_g, sp, ep, kdim / kBK));
     if (prof_on) {
         long long h[8 * 256];
         OFX_CUDA(cudaStreamSynchronize(stream));
@@ -605,16 +611,16 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
     int* cand_i = reinterpret_cast<int*>(ws + W.cand_i);
 
     if (n_rows > 0) {
-        const long long nq_el = static_cast<long long>(n_query) * dim;
-        to_bf16_kernel<<<static_cast<unsigned>((nq_el / 4 + 255) / 256), 256, 0, st>>>(queries, nq_el, q_bf16);
+        const long long nq_el = static_cast<long long>(n_query) * (dim + kAugCols);
+        to_bf16_kernel<<<static_cast<unsigned>((nq_el / 4 + 255) / 256), 256, 0, st>>>(
+            queries, n_query, dim, metric == OFX_METRIC_L2 ? 1.f : 0.f, q_bf16);
         OFX_LAUNCH_CHECK();
         OFX_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(W.plan.n_qgroups) * W.plan.cl * 128 * 4, st));
-        const float* half = metric == OFX_METRIC_L2 ? reinterpret_cast<const float*>(pk + L.rows_bytes) : nullptr;
         if (W.kcap == 32) {
-            EpiTopK<32>::Params ep{half, n_rows, n_query, thr, cand_s, cand_i, cand_n};
+            EpiTopK<32>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n};
             OFX_TRY((launch_search_cl<32, 4>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         } else {
-            EpiTopK<64>::Params ep{half, n_rows, n_query, thr, cand_s, cand_i, cand_n};
+            EpiTopK<64>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n};
             OFX_TRY((launch_search_cl<64, 3>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         }
     }
