@@ -374,6 +374,27 @@ def main():
     e2e_ms = timed(cp_e2e_step, args.steps, 2, dist_ok, dev)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
 
+    # the same step with the collate on the device: item tables resident in HBM, only
+    # item ids / masks / text prefixes / candidate ids cross PCIe.  Reported beside `e2e`, not as it.
+    n_table = 200_000
+    g2 = torch.Generator(device=dev).manual_seed(77 + rank)
+    tab_img = torch.randn(n_table, DPM, device=dev, generator=g2)
+    tab_txt = torch.randn(n_table, DPM, device=dev, generator=g2)
+    tab_cand = torch.nn.functional.normalize(torch.randn(n_table, 2, DPM, device=dev, generator=g2), dim=-1)
+    tab_cand = tab_cand.reshape(n_table, 2 * DPM).contiguous()
+    ids_host = torch.randint(0, n_table, (B, 16), dtype=torch.int32).pin_memory()
+    cids_host = torch.randint(0, n_table, (B, N_CAND), dtype=torch.int32).pin_memory()
+    ids_h2d = ids_host.numel() * 4 + cids_host.numel() * 4 + host["mask"].numel() + host["text"].numel() * 4
+
+    pipe_ids = HostScoringPipeline(model, chunk=B)   # ids are 64 B per outfit: nothing to overlap, one chunk
+
+    def cp_e2e_ids_step():
+        pipe_ids.score_ids(ids_host, host["mask"], tab_img, tab_txt, host["text"], cids_host, tab_cand, out=res_host)
+
+    e2e_ids_ms = timed(cp_e2e_ids_step, args.steps, 2, dist_ok, dev)
+    e2e_ids_value = world * B * args.steps / (e2e_ids_ms * 1e-3)
+    del tab_img, tab_txt, tab_cand
+
     # ------------------------------------------------------------------ CIR (secondary, sharded)
     cir = None
     if not args.no_cir:
@@ -457,7 +478,13 @@ def main():
             "roofline_step": {"bound": "tensor", "achieved": cp_tflops, "peak": pk["burst"], "unit": "TFLOP/s",
                               "frac": cp_tflops / pk["burst"], "flops_per_step": flops_step,
                               "kernel": "whole step, all launches (flops_alg: minimum exact work, SURVEY 8d)"},
-            "e2e": {"value": e2e_value, "unit": "outfits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "outfits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "outfitx_b200.pipeline.HostScoringPipeline.score: fp32 (B,16,512) image + text embeddings "
+                           "from pinned host memory, chunked H2D overlapped with scoring"},
+            "e2e_device_collate": {"value": e2e_ids_value, "unit": "outfits/s", "h2d_bytes_per_step": ids_h2d,
+                                   "d2h_bytes_per_step": d2h,
+                                   "api": "HostScoringPipeline.score_ids: item ids from host, 200k-item embedding "
+                                          "tables resident in HBM (SURVEY.md N2)"},
             "gpu_launches": int(launches_cp),
             "cpu_baseline": cpu,
             "cir": cir,

@@ -137,6 +137,15 @@ typedef struct ofx_forward_args {
     int32_t n_cand;        /* 4 in the reference                                      */
     float* fitb_dist;      /* FITB out: (B, n_cand) L2 distances, may be NULL         */
     int64_t* fitb_argmin;  /* FITB out: (B) first-minimum index                       */
+    /* Device-side collate (replaces the per-batch gather + pad of the reference's processors,
+     * src/models/processor/outfit_x/outfit_x_base_processor.py:20-81): when item_ids != NULL,
+     * img / txt are TABLES (n_table_rows, dpm) resident in HBM and slot (b, s) reads row
+     * item_ids[b * max_items + s]; ids of padded slots are ignored, ids outside the table read
+     * as zero rows.  Likewise cand is a table (n_cand_rows, De) when cand_ids != NULL.        */
+    const int32_t* item_ids;   /* (B, max_items) or NULL                              */
+    int64_t n_table_rows;
+    const int32_t* cand_ids;   /* (B, n_cand) or NULL                                 */
+    int64_t n_cand_rows;
 } ofx_forward_args;
 
 OFX_API size_t ofx_encoder_workspace_bytes(const ofx_shape* shape, int32_t batch);

@@ -44,7 +44,9 @@ class ForwardArgs(C.Structure):
                 ("txt", C.c_void_p), ("fuse_mode", C.c_int32), ("normalize", C.c_int32),
                 ("mask", C.c_void_p), ("text", C.c_void_p), ("logits", C.c_void_p),
                 ("probs", C.c_void_p), ("query", C.c_void_p), ("cand", C.c_void_p),
-                ("n_cand", C.c_int32), ("fitb_dist", C.c_void_p), ("fitb_argmin", C.c_void_p)]
+                ("n_cand", C.c_int32), ("fitb_dist", C.c_void_p), ("fitb_argmin", C.c_void_p),
+                ("item_ids", C.c_void_p), ("n_table_rows", C.c_int64),
+                ("cand_ids", C.c_void_p), ("n_cand_rows", C.c_int64)]
 
 
 _SIGNATURES = {

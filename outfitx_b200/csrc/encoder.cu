@@ -164,6 +164,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
     as.text = a->text;
     as.ln_w = lf(0, L.ln1w); as.ln_b = lf(0, L.ln1b);
     as.owner = owner;
+    as.item_ids = a->item_ids; as.n_table_rows = a->n_table_rows;
     OFX_TRY(assemble<T>(as, dm, x, h, st));
 
     for (int l = 0; l < L.nl; ++l) {
@@ -228,7 +229,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
         GemmArgs gc{q0, dm, wts + L.g_cir, dm, B, nullptr, L.de, dm, nullptr, 0, nullptr, 0, a->query, L.de, 1};
         OFX_TRY(gemm<T>(gc, st));
         if (a->cand)
-            OFX_TRY(fitb(a->query, a->cand, B, a->n_cand, L.de, a->fitb_dist,
+            OFX_TRY(fitb(a->query, a->cand, a->cand_ids, a->n_cand_rows, B, a->n_cand, L.de, a->fitb_dist,
                          reinterpret_cast<long long*>(a->fitb_argmin), st));
     }
     return OFX_OK;
@@ -279,6 +280,10 @@ int ofx_encoder_forward(const ofx_shape* shape, const void* packed_weights, cons
         return fail(OFX_E_ARG, "CIR needs target_item_text_embedding and a query output");
     if (a->cand && (a->n_cand < 1 || (!a->fitb_dist && !a->fitb_argmin)))
         return fail(OFX_E_ARG, "FITB needs n_cand >= 1 and an output");
+    if (a->item_ids && (a->emb || !a->img || !a->txt || a->n_table_rows < 1))
+        return fail(OFX_E_ARG, "item_ids needs img / txt tables with n_table_rows >= 1 (and no outfit_embedding)");
+    if (a->cand_ids && (!a->cand || a->n_cand_rows < 1))
+        return fail(OFX_E_ARG, "cand_ids needs a candidate table with n_cand_rows >= 1");
     if (reinterpret_cast<uintptr_t>(a->emb) % 16 || reinterpret_cast<uintptr_t>(a->img) % 16 ||
         reinterpret_cast<uintptr_t>(a->txt) % 16 || reinterpret_cast<uintptr_t>(a->text) % 16 ||
         reinterpret_cast<uintptr_t>(a->cand) % 16 || reinterpret_cast<uintptr_t>(a->query) % 16 ||

@@ -244,7 +244,13 @@ assemble_kernel(AssembleArgs a, float* __restrict__ x, T* __restrict__ h) {
         for (int j = 0; j < s - 1; ++j) rank += m[j] == 0;
         row = a.batch + a.off[b] + rank;
         if (lane == 0) a.owner[row] = b;
-        const long long item = static_cast<long long>(b) * a.max_items + (s - 1);
+        long long item = static_cast<long long>(b) * a.max_items + (s - 1);
+        bool in_table = true;
+        if (a.item_ids) {            // device-side collate: the slot names a row of the item tables
+            item = a.item_ids[item];
+            in_table = item >= 0 && item < a.n_table_rows;
+            if (!in_table) item = 0;
+        }
         if (a.emb) {
 #pragma unroll
             for (int i = 0; i < NV; ++i)
@@ -252,6 +258,10 @@ assemble_kernel(AssembleArgs a, float* __restrict__ x, T* __restrict__ h) {
         } else {
             load_fused_row<DM>(v, a.img + item * a.dpm, a.txt + item * a.dpm, a.dpm, a.fuse_mode,
                                a.normalize, lane);
+        }
+        if (!in_table) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 #pragma unroll
@@ -751,19 +761,27 @@ int cp_head(const float* x0, int batch, int dm, const float* w, const float* bia
 // ------------------------------------------------------------------ FITB: warp per outfit
 // d_j = || q - c_j ||_2 (direct differences, like torch.cdist for small inputs), argmin = first minimum
 __global__ void __launch_bounds__(256)
-fitb_kernel(const float* __restrict__ query, const float* __restrict__ cand, int batch, int n_cand,
-            int de, float* __restrict__ dist, long long* __restrict__ argmin) {
+fitb_kernel(const float* __restrict__ query, const float* __restrict__ cand, const int* __restrict__ cand_ids,
+            long long n_cand_rows, int batch, int n_cand, int de, float* __restrict__ dist,
+            long long* __restrict__ argmin) {
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= batch) return;
     const int lane = threadIdx.x & 31;
     float best = INFINITY;
     int best_j = 0;
     for (int j = 0; j < n_cand; ++j) {
-        const float* c = cand + (static_cast<long long>(b) * n_cand + j) * de;
+        long long crow = static_cast<long long>(b) * n_cand + j;
+        bool in_table = true;
+        if (cand_ids) {
+            crow = cand_ids[crow];
+            in_table = crow >= 0 && crow < n_cand_rows;
+            if (!in_table) crow = 0;
+        }
+        const float* c = cand + crow * de;
         float s = 0.f;
         for (int e = lane * 4; e < de; e += 128) {
             float4 qv = *reinterpret_cast<const float4*>(query + static_cast<long long>(b) * de + e);
-            float4 cv = *reinterpret_cast<const float4*>(c + e);
+            float4 cv = in_table ? *reinterpret_cast<const float4*>(c + e) : make_float4(0.f, 0.f, 0.f, 0.f);
             float d0 = qv.x - cv.x, d1 = qv.y - cv.y, d2 = qv.z - cv.z, d3 = qv.w - cv.w;
             s += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
         }
@@ -773,10 +791,11 @@ fitb_kernel(const float* __restrict__ query, const float* __restrict__ cand, int
     }
     if (lane == 0 && argmin) argmin[b] = best_j;
 }
-int fitb(const float* query, const float* cand, int batch, int n_cand, int de, float* dist,
-         long long* argmin, cudaStream_t stream) {
+int fitb(const float* query, const float* cand, const int* cand_ids, long long n_cand_rows, int batch,
+         int n_cand, int de, float* dist, long long* argmin, cudaStream_t stream) {
     if (batch <= 0) return OFX_OK;
-    fitb_kernel<<<(batch + 7) / 8, 256, 0, stream>>>(query, cand, batch, n_cand, de, dist, argmin);
+    fitb_kernel<<<(batch + 7) / 8, 256, 0, stream>>>(query, cand, cand_ids, n_cand_rows, batch, n_cand, de, dist,
+                                                     argmin);
     OFX_LAUNCH_CHECK();
     return OFX_OK;
 }

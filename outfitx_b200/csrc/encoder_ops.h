@@ -17,6 +17,8 @@ struct AssembleArgs {
     const float* ln_w;          // LayerNorm 1 of layer 0 (fused here)
     const float* ln_b;
     int* owner;                 // out: (B + total items) token row -> outfit (item rows only)
+    const int* item_ids;        // optional (B, max_items): img / txt are tables, slot -> table row
+    long long n_table_rows;
 };
 
 struct AttnArgs {
@@ -58,8 +60,8 @@ template <class T> int cast_rows(const float* in, long long n, T* out, cudaStrea
 template <class T> int attention(const AttnArgs& a, int head_dim, cudaStream_t stream);
 int cp_head(const float* x0, int batch, int dm, const float* w, const float* bias, float* logits,
             float* probs, cudaStream_t stream);
-int fitb(const float* query, const float* cand, int batch, int n_cand, int de, float* dist,
-         long long* argmin, cudaStream_t stream);
+int fitb(const float* query, const float* cand, const int* cand_ids, long long n_cand_rows, int batch,
+         int n_cand, int de, float* dist, long long* argmin, cudaStream_t stream);
 template <class T> int pack_matrix(const float* src, int rows, int cols, T* dst, int prow, int pcol,
                                    cudaStream_t stream);
 

@@ -229,7 +229,8 @@ class OutfitX(nn.Module):
         L = _lib.lib()
         shape = self._shape()
         d = shape.d_model
-        img = txt = None
+        img = txt = item_ids = cand_ids = None
+        n_table = 0
         fuse_mode, normalize = _lib.FUSE_CONCAT, 1
         if enc_dict is not None:
             try:
@@ -244,11 +245,23 @@ class OutfitX(nn.Module):
             normalize = int(enc_dict.get("normalize", self.cfg.item_encoder.norm_out))
             img, txt = self._f32(img, "image_embeddings"), self._f32(txt, "text_embeddings")
             dpm = self.cfg.item_encoder.dim_per_modality
-            if img.shape != txt.shape or img.dim() != 3 or img.shape[-1] != dpm:
-                raise ValueError(f"image/text embeddings must both be (B, L, {dpm})")
             if (2 * dpm if method == "concat" else dpm) != d:
                 raise ValueError(f"aggregation '{method}' gives width != d_model {d}")
-            B, n_items = img.shape[0], img.shape[1]
+            item_ids = enc_dict.get("item_ids")
+            if item_ids is not None:
+                # device-side collate: image / text embeddings are item TABLES
+                # (n_items, dpm) resident in HBM, item_ids (B, L) selects the rows of each slot
+                if img.shape != txt.shape or img.dim() != 2 or img.shape[-1] != dpm:
+                    raise ValueError(f"with item_ids, image/text embeddings must both be tables (n_items, {dpm})")
+                if not item_ids.is_cuda or item_ids.dim() != 2:
+                    raise ValueError("item_ids must be a CUDA tensor (B, L)")
+                item_ids = item_ids.to(torch.int32).contiguous()
+                B, n_items = item_ids.shape
+                n_table = img.shape[0]
+            else:
+                if img.shape != txt.shape or img.dim() != 3 or img.shape[-1] != dpm:
+                    raise ValueError(f"image/text embeddings must both be (B, L, {dpm})")
+                B, n_items = img.shape[0], img.shape[1]
             dev = img.device
             emb = None
         else:
@@ -276,7 +289,9 @@ class OutfitX(nn.Module):
         args.txt = txt.data_ptr() if txt is not None else None
         args.fuse_mode, args.normalize = fuse_mode, normalize
         args.mask = mask_u8.data_ptr()
-        keep = [emb, img, txt, mask_u8]
+        if item_ids is not None:
+            args.item_ids, args.n_table_rows = item_ids.data_ptr(), n_table
+        keep = [emb, img, txt, mask_u8, item_ids]
         if task == _lib.TASK_CP:
             out["logits"] = torch.empty(B, dtype=torch.float32, device=dev)
             args.logits = out["logits"].data_ptr()
@@ -294,11 +309,24 @@ class OutfitX(nn.Module):
             args.query = out["query"].data_ptr()
             keep.append(text)
             if cand is not None:
-                cand = self._f32(cand, "candidate_item_embedding")
-                if cand.dim() != 3 or cand.shape[0] != B or cand.shape[2] != shape.d_embed:
-                    raise ValueError(f"candidate_item_embedding must be ({B}, n_cand, {shape.d_embed})")
-                args.cand, args.n_cand = cand.data_ptr(), cand.shape[1]
-                out["fitb_dist"] = torch.empty(B, cand.shape[1], dtype=torch.float32, device=dev)
+                if isinstance(cand, (tuple, list)):        # (table (n_rows, De), ids (B, n_cand))
+                    cand, cand_ids = cand
+                    cand = self._f32(cand, "candidate table")
+                    if cand.dim() != 2 or cand.shape[1] != shape.d_embed:
+                        raise ValueError(f"candidate table must be (n_rows, {shape.d_embed})")
+                    if not cand_ids.is_cuda or cand_ids.dim() != 2 or cand_ids.shape[0] != B:
+                        raise ValueError(f"candidate ids must be a CUDA tensor ({B}, n_cand)")
+                    cand_ids = cand_ids.to(torch.int32).contiguous()
+                    n_cand = cand_ids.shape[1]
+                    args.cand_ids, args.n_cand_rows = cand_ids.data_ptr(), cand.shape[0]
+                    keep.append(cand_ids)
+                else:
+                    cand = self._f32(cand, "candidate_item_embedding")
+                    if cand.dim() != 3 or cand.shape[0] != B or cand.shape[2] != shape.d_embed:
+                        raise ValueError(f"candidate_item_embedding must be ({B}, n_cand, {shape.d_embed})")
+                    n_cand = cand.shape[1]
+                args.cand, args.n_cand = cand.data_ptr(), n_cand
+                out["fitb_dist"] = torch.empty(B, n_cand, dtype=torch.float32, device=dev)
                 out["fitb_argmin"] = torch.empty(B, dtype=torch.int64, device=dev)
                 args.fitb_dist = out["fitb_dist"].data_ptr()
                 args.fitb_argmin = out["fitb_argmin"].data_ptr()

@@ -92,3 +92,51 @@ class HostScoringPipeline:
         cur.wait_stream(self.compute_stream)
         self.compute_stream.synchronize()
         return out
+
+    @torch.no_grad()
+    def score_ids(self, item_ids: torch.Tensor, outfit_mask: torch.Tensor, image_table: torch.Tensor,
+                  text_table: torch.Tensor, target_item_text_embedding: Optional[torch.Tensor] = None,
+                  candidate_ids: Optional[torch.Tensor] = None, candidate_table: Optional[torch.Tensor] = None,
+                  out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """As ``score`` but with the collate on the device: the item embedding tables
+        ``(n_items, dim_per_modality)`` [and the fused candidate table ``(n_items, d_embed)``] are
+        DEVICE tensors resident in HBM -- the counterpart of the embedding dict the reference's
+        trainers keep in host memory (``compatibility_prediction_trainer.py:329-349``) -- and a
+        batch is ``item_ids (B, L)`` int32 + ``outfit_mask`` [+ ``candidate_ids (B, n_cand)``] on the
+        HOST.  Only ids cross PCIe (64 B per outfit instead of 64 KB)."""
+        B = item_ids.shape[0]
+        fitb = candidate_ids is not None
+        if fitb and (target_item_text_embedding is None or candidate_table is None):
+            raise ValueError("FITB scoring needs target_item_text_embedding and candidate_table")
+        if out is None:
+            out = {"probs": torch.empty(B, dtype=torch.float32).pin_memory()}
+            if fitb:
+                out["pred"] = torch.empty(B, dtype=torch.int64).pin_memory()
+        cur = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(cur)
+        self.compute_stream.wait_stream(cur)
+        for i, lo in enumerate(range(0, B, self.chunk)):
+            hi = min(B, lo + self.chunk)
+            s = i & 1
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(self._free[s])
+                d = {"ids": self._stage(s, "ids", item_ids[lo:hi]), "mask": self._stage(s, "idmask", outfit_mask[lo:hi])}
+                if fitb:
+                    d["text"] = self._stage(s, "text", target_item_text_embedding[lo:hi])
+                    d["cids"] = self._stage(s, "cids", candidate_ids[lo:hi])
+                self._ready[s].record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(self._ready[s])
+                enc = {"image_embeddings": image_table, "text_embeddings": text_table, "item_ids": d["ids"]}
+                probs = self.model.score_cp(outfit_mask=d["mask"], encoder_input_dict=enc)
+                out["probs"][lo:hi].copy_(probs, non_blocking=True)
+                if fitb:
+                    pred, _, _ = self.model.score_fitb(outfit_mask=d["mask"], target_item_text_embedding=d["text"],
+                                                       candidate_item_embedding=(candidate_table, d["cids"]),
+                                                       encoder_input_dict=enc)
+                    out["pred"][lo:hi].copy_(pred, non_blocking=True)
+                self._free[s].record(self.compute_stream)
+        cur.wait_stream(self.compute_stream)
+        self.compute_stream.synchronize()
+        return out

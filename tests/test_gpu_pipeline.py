@@ -34,3 +34,42 @@ def test_pipeline_equals_direct_calls(batch, chunk):
     cp_only = HostScoringPipeline(m, chunk=chunk).score(host[0], host[1], host[2])
     torch.testing.assert_close(cp_only["probs"], probs.cpu(), rtol=0, atol=1e-6)
     assert "pred" not in cp_only
+
+
+def test_device_side_collate_equals_host_gather():
+    """item-id gather from HBM-resident tables == the reference-style padded batch
+    built on the host (outfit_x_base_processor.py:20-43), through the model API and the pipeline."""
+    import outfitx_b200 as o
+    from outfitx_b200.pipeline import HostScoringPipeline
+    sd = synth.make_state_dict(512, 1024, seed=0)
+    m = o.OutfitX(o.OutfitXConfig(item_encoder=o.ItemEncoderConfig(type="clip", aggregation_method="mean")))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.to("cuda")
+    n_items, B = 5000, 333
+    rng = np.random.Generator(np.random.PCG64(7))
+    img_t = rng.standard_normal((n_items, 512)).astype(np.float32)
+    txt_t = rng.standard_normal((n_items, 512)).astype(np.float32)
+    cand_t = synth.make_items(n_items, 512, seed=8)                       # fused 1024-d candidates
+    ids = rng.integers(0, n_items, size=(B, 16)).astype(np.int32)
+    cids = rng.integers(0, n_items, size=(B, 4)).astype(np.int32)
+    mask = synth.make_mask(synth.make_lengths(B, 9))
+    ids[mask] = -1                                                          # padded slots: any id
+    text = synth.make_text_prefix(B, 256, 10)
+    safe = np.where(ids < 0, 0, ids)
+    dense = [torch.from_numpy(a).cuda() for a in (img_t[safe], txt_t[safe], mask, text, cand_t[cids])]
+    enc = {"image_embeddings": dense[0], "text_embeddings": dense[1]}
+    want_p = m.score_cp(outfit_mask=dense[2], encoder_input_dict=enc)
+    want_pred, want_d, _ = m.score_fitb(outfit_mask=dense[2], target_item_text_embedding=dense[3],
+                                        candidate_item_embedding=dense[4], encoder_input_dict=enc)
+    tabs = [torch.from_numpy(a).cuda() for a in (img_t, txt_t, cand_t)]
+    enc_ids = {"image_embeddings": tabs[0], "text_embeddings": tabs[1], "item_ids": torch.from_numpy(ids).cuda()}
+    got_p = m.score_cp(outfit_mask=dense[2], encoder_input_dict=enc_ids)
+    got_pred, got_d, _ = m.score_fitb(outfit_mask=dense[2], target_item_text_embedding=dense[3],
+                                      candidate_item_embedding=(tabs[2], torch.from_numpy(cids).cuda()),
+                                      encoder_input_dict=enc_ids)
+    assert torch.equal(got_p, want_p) and torch.equal(got_pred, want_pred) and torch.equal(got_d, want_d)
+    pipe = HostScoringPipeline(m, chunk=128)
+    host = [torch.from_numpy(a).pin_memory() for a in (ids, mask, text, cids)]
+    out = pipe.score_ids(host[0], host[1], tabs[0], tabs[1], host[2], host[3], tabs[2])
+    torch.testing.assert_close(out["probs"], want_p.cpu(), rtol=0, atol=1e-6)
+    assert torch.equal(out["pred"], want_pred.cpu())
