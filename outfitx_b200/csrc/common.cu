@@ -61,7 +61,7 @@ int cluster_size() {
         cl = 2;
         if (const char* e = getenv("OFX_CLUSTER")) {
             const int v = atoi(e);
-            if (v == 1 || v == 2 || v == 4) cl = v;
+            if (v == 1 || v == 2) cl = v;
         }
     }
     return cl;

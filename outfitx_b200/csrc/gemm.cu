@@ -247,13 +247,15 @@ template <int BN, int CL, class Epi>
 static int launch_tc(const GemmArgs& g, cudaStream_t stream) {
     CUtensorMap tm_a, tm_b;
     OFX_TRY(make_tmap_bf16(&tm_a, g.a, static_cast<uint64_t>(g.m), g.k, g.lda, kBM));
-    OFX_TRY(make_tmap_bf16(&tm_b, g.w, static_cast<uint64_t>(g.n), g.k, g.ldw, BN / CL));
+    OFX_TRY(make_tmap_bf16(&tm_b, g.w, static_cast<uint64_t>(g.n), g.k, g.ldw, BN / CL));   // each CTA fetches BN / CL rows
     SchedGemm::Params sp{g.m, g.m_dev, g.n / BN, BN, CL};
     typename Epi::Params ep;
     OFX_TRY(make_epi_params<BN>(g, &ep));
-    constexpr int kStages = BN >= 256 ? 4 : 5;
-    auto kern = tc_kernel<BN, kStages, CL, SchedGemm, Epi>;
-    constexpr int smem = tc_smem_bytes<BN, kStages, Epi>();
+    // stage = 16 KB of A + (BN / CL) rows of B: 48 KB single-CTA, 32 KB per CTA of a pair at BN = 256
+    constexpr int kStages = BN >= 256 ? (CL == 2 ? 6 : 4) : (CL == 2 ? 7 : 5);
+    constexpr bool kPair = CL == 2;    // the linear layers run as CTA pairs (QKV: 116 -> 102 us at 82k tokens)
+    auto kern = tc_kernel<BN, kStages, CL, SchedGemm, Epi, kPair>;
+    constexpr int smem = tc_smem_bytes<BN, kStages, Epi, kPair>();
     static bool configured = false;  // per instantiation
     if (!configured) {
         OFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -299,21 +301,15 @@ template <int BN>
 static int launch_tc_cl(const GemmArgs& g, cudaStream_t stream) {
     const long long m_tiles = (g.m + kBM - 1) / kBM;
     int cl = cluster_size();
-    while (cl > 1 && m_tiles < cl) cl >>= 1;  // tiny M: nothing to share
+    if (m_tiles < 2) cl = 1;  // a single M tile: nothing to pair
     // bf16 output without residual (QKV, linear1): TMA-store epilogue; otherwise the fp32 / residual one
     const bool bf16_store = !g.out_f32 && !g.residual;
     if (bf16_store) {
-        switch (cl) {
-            case 4: return launch_tc<BN, 4, EpiStoreBf16<BN>>(g, stream);
-            case 2: return launch_tc<BN, 2, EpiStoreBf16<BN>>(g, stream);
-            default: return launch_tc<BN, 1, EpiStoreBf16<BN>>(g, stream);
-        }
+        if (cl == 2) return launch_tc<BN, 2, EpiStoreBf16<BN>>(g, stream);
+        return launch_tc<BN, 1, EpiStoreBf16<BN>>(g, stream);
     }
-    switch (cl) {
-        case 4: return launch_tc<BN, 4, EpiLinear<BN>>(g, stream);
-        case 2: return launch_tc<BN, 2, EpiLinear<BN>>(g, stream);
-        default: return launch_tc<BN, 1, EpiLinear<BN>>(g, stream);
-    }
+    if (cl == 2) return launch_tc<BN, 2, EpiLinear<BN>>(g, stream);
+    return launch_tc<BN, 1, EpiLinear<BN>>(g, stream);
 }
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {

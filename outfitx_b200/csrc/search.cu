@@ -113,7 +113,7 @@ static SearchPlan make_plan(long long n_rows, int n_query, int n_sm) {
     SearchPlan pl{};
     pl.n_qblocks = (n_query + kBM - 1) / kBM;
     pl.cl = cluster_size();
-    while (pl.cl > 1 && pl.n_qblocks < pl.cl) pl.cl >>= 1;
+    if (pl.n_qblocks < 2) pl.cl = 1;
     pl.n_qgroups = (pl.n_qblocks + pl.cl - 1) / pl.cl;
     const int n_cta = n_sm / pl.cl;  // clusters that fit
     pl.n_tiles = static_cast<int>((n_rows + kSearchBN - 1) / kSearchBN);
@@ -497,8 +497,8 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     const int kdim = dim + kAugCols;   // contraction length including the bias k-block
     OFX_TRY(make_tmap_bf16(&tm_q, q_bf16, static_cast<uint64_t>(n_query), kdim, kdim, kBM));
     OFX_TRY(make_tmap_bf16(&tm_g, gallery, static_cast<uint64_t>(n_rows), kdim, kdim, kSearchBN / CL));
-    auto kern = tc_kernel<kSearchBN, STAGES, CL, SchedSearch, Epi>;
-    constexpr int smem = tc_smem_bytes<kSearchBN, STAGES, Epi>();
+    auto kern = tc_kernel<kSearchBN, STAGES, CL, SchedSearch, Epi, false>;   // CL = 2: multicast cluster
+    constexpr int smem = tc_smem_bytes<kSearchBN, STAGES, Epi, false>();
     static bool configured = false;
     if (!configured) {
         OFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -541,11 +541,8 @@ template <int KCAP, int STAGES>
 static int launch_search_cl(const void* q_bf16, int n_query, const void* gallery, long long n_rows,
                             const SearchPlan& pl, const typename EpiTopK<KCAP>::Params& ep, int dim,
                             cudaStream_t stream) {
-    switch (pl.cl) {
-        case 4: return launch_search<KCAP, STAGES, 4>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
-        case 2: return launch_search<KCAP, STAGES, 2>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
-        default: return launch_search<KCAP, STAGES, 1>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
-    }
+    if (pl.cl == 2) return launch_search<KCAP, STAGES, 2>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
+    return launch_search<KCAP, STAGES, 1>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
 }
 
 }  // namespace ofx

@@ -13,12 +13,17 @@
 // Three barrier rings: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 // The tile sequence comes from a Sched object that all roles evaluate identically.
 //
-// CL > 1: thread-block clusters of CL CTAs that work on the SAME B tile (n0) with different A
-// tiles (m0).  Each CTA fetches 1/CL of the B tile and TMA-multicasts it into every CTA of the
-// cluster, so a B tile crosses the L2 -> SM fabric once per cluster instead of once per CTA.
-// A stage may be refilled only when every CTA of the cluster has consumed it (all of them are
-// written by each multicast), hence empty barriers count CL arrivals and the MMA commit is
-// multicast to all CTAs.  The Sched must give all CTAs of a cluster the same tile count and n0.
+// CL == 2, PAIR = false: a multicast cluster -- two CTAs with different A tiles and the SAME B tile;
+// each fetches half of the B rows and TMA-multicasts them into both, every CTA issues its own
+// M = 128 MMAs.  (Best for the search kernel: measured 1004 vs 940 TFLOP/s at 10 M rows.)
+// CL == 2, PAIR = true: a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  The two CTAs own consecutive M
+// tiles (256 rows together) and the same B tile (n0); the even CTA issues M = 256 MMAs, each CTA
+// supplies its own 128 rows of A and HALF of the B tile from its own shared memory and receives
+// its 128 accumulator rows in its own TMEM.  Against two independent CTAs (or a multicast
+// cluster, which still parks the whole B tile in both CTAs) this cuts the shared-memory traffic
+// per SM from 192 B/clk (96 operand reads + 96 TMA fills at full tensor rate, above the 128 B/clk
+// the SM can move) to 128 B/clk, and the stage footprint from 48 KB to 32 KB (6 stages).
+// The Sched must give both CTAs of a pair the same tile count and n0.
 #pragma once
 #include <cuda.h>
 
@@ -31,10 +36,10 @@ constexpr int kBK = 64;        // bf16 elements per smem row = 128 B = one swizz
 constexpr int kUmmaK = 16;     // K per tcgen05.mma for 16-bit inputs
 constexpr int kEpiWarp0 = 4;   // first epilogue warp (warp % 4 selects the TMEM lane quarter)
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 struct TcCfg {
     static constexpr int kABytes = kBM * kBK * 2;
-    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 2;   // pair: each CTA holds half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = STAGES;
     static constexpr int kTmemCols = 2 * BN;  // power of two for BN in {64,128,256}
@@ -42,9 +47,9 @@ struct TcCfg {
     static constexpr int kBarBytes = 1024;  // barriers + tmem slot; keeps the epilogue smem 1024-byte aligned (TMA swizzle)
 };
 
-template <int BN, int STAGES, class Epi>
+template <int BN, int STAGES, class Epi, bool PAIR = false>
 constexpr int tc_smem_bytes() {
-    return 1024 /*alignment slack*/ + TcCfg<BN, STAGES>::kRingBytes + TcCfg<BN, STAGES>::kBarBytes +
+    return 1024 /*alignment slack*/ + TcCfg<BN, STAGES, PAIR>::kRingBytes + TcCfg<BN, STAGES, PAIR>::kBarBytes +
            Epi::kSmemBytes;
 }
 
@@ -68,12 +73,17 @@ constexpr int tc_threads() { return 128 + 32 * Epi::kWarps; }
 // {total, wait smem-full, wait tmem-empty} and of epilogue warp 0 {total, wait tmem-full}.
 __device__ long long* g_tc_prof = nullptr;
 
-template <int BN, int STAGES, int CL, class Sched, class Epi>
+template <int BN, int STAGES, int CL, class Sched, class Epi, bool PAIR = false>
 __global__ void __launch_bounds__(128 + 32 * Epi::kWarps, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
           const typename Sched::Params sp, const __grid_constant__ typename Epi::Params ep,
           const int num_k_blocks) {
-    using Cfg = TcCfg<BN, STAGES>;
+    static_assert(CL == 1 || CL == 2, "CL = 1 (single CTA) or 2 (multicast cluster or CTA pair)");
+    static_assert(!PAIR || CL == 2, "a pair is a cluster of 2");
+    using Cfg = TcCfg<BN, STAGES, PAIR>;
+    constexpr bool kPair = PAIR;
+    constexpr bool kMcast = CL == 2 && !PAIR;   // B tile multicast into both CTAs, independent MMAs
+    constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte aligned bases
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -90,8 +100,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-    constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << CL) - 1u);
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;   // pair: 0 = leader (issues the MMAs)
     constexpr int kBRowsPerCta = BN / CL;  // rows of the B tile this CTA fetches
 
     if (warp == 0 && lane == 0) {
@@ -100,16 +109,19 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], CL);
+            mbar_init(&full[i], 1);     // pair: the leader's collects the bytes of both CTAs
+            mbar_init(&empty[i], kMcast ? CL : 1);   // multicast: every CTA's MMAs must retire before a refill
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], Epi::kWarps);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], Epi::kWarps * (kPair ? 2 : 1));  // one arrive per epilogue warp (pair: of both CTAs, on the leader's)
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    if (warp == 2) {
+        if constexpr (kPair) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+        else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
     if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before any remote use
@@ -125,13 +137,22 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             while (sched.next()) {
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-                    tma_load_2d(s_a + stage * Cfg::kABytes, &tm_a, &full[stage], kb * kBK, sched.m0);
-                    if constexpr (CL == 1) {
-                        tma_load_2d(s_b + stage * Cfg::kBBytes, &tm_b, &full[stage], kb * kBK, sched.n0);
+                    if constexpr (!kPair) {
+                        mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+                        tma_load_2d(s_a + stage * Cfg::kABytes, &tm_a, &full[stage], kb * kBK, sched.m0);
+                        if constexpr (!kMcast) {
+                            tma_load_2d(s_b + stage * Cfg::kBBytes, &tm_b, &full[stage], kb * kBK, sched.n0);
+                        } else {   // this CTA's half of the B rows lands in BOTH CTAs (and signals both barriers)
+                            tma_load_2d_mc(s_b + stage * Cfg::kBBytes + crank * (kBRowsPerCta * kBK * 2), &tm_b,
+                                           &full[stage], kb * kBK, sched.n0 + crank * kBRowsPerCta, kAllCtas);
+                        }
                     } else {
-                        tma_load_2d_mc(s_b + stage * Cfg::kBBytes + crank * (kBRowsPerCta * kBK * 2), &tm_b,
-                                       &full[stage], kb * kBK, sched.n0 + crank * kBRowsPerCta, kAllCtas);
+                        // both CTAs' bytes are accounted on the leader's barrier
+                        if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+                        const uint32_t bar = mapa_shared(smem_u32(&full[stage]), 0);
+                        tma_load_2d_pair(s_a + stage * Cfg::kABytes, &tm_a, bar, kb * kBK, sched.m0, kEvictNormal);
+                        tma_load_2d_pair(s_b + stage * Cfg::kBBytes, &tm_b, bar, kb * kBK,
+                                         sched.n0 + static_cast<int>(crank) * kBRowsPerCta, kEvictNormal);
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -143,8 +164,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         // descriptors in uniform registers); one elected lane issues the tcgen05 instructions
         // back to back.  A lane-0-only loop costs ~20 issue slots per MMA in address traffic
         // between the vector and uniform register files.
-        {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+        if (!kPair || crank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kPair ? 2 * kBM : kBM, BN);
             constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SW128
             const uint32_t a_lo0 = ((smem_u32(s_a) & 0x3FFFF) >> 4) | (1u << 16);
             const uint32_t b_lo0 = ((smem_u32(s_b) & 0x3FFFF) >> 4) | (1u << 16);
@@ -167,17 +188,26 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                     const uint32_t b_lo = b_lo0 + stage * (Cfg::kBBytes >> 4);
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kBK / kUmmaK; ++k)
-                            umma_bf16(d_tmem, desc(a_lo + k * (kUmmaK * 2 >> 4)), desc(b_lo + k * (kUmmaK * 2 >> 4)),
-                                      idesc, (kb | k) != 0 ? 1u : 0u);
-                        // frees the smem slot (in every CTA of the cluster) when the MMAs retire
-                        if constexpr (CL == 1) umma_commit(&empty[stage]);
-                        else umma_commit_mc(&empty[stage], kAllCtas);
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            if constexpr (kPair)
+                                umma_bf16_pair(d_tmem, desc(a_lo + k * (kUmmaK * 2 >> 4)), desc(b_lo + k * (kUmmaK * 2 >> 4)),
+                                               idesc, (kb | k) != 0 ? 1u : 0u);
+                            else
+                                umma_bf16(d_tmem, desc(a_lo + k * (kUmmaK * 2 >> 4)), desc(b_lo + k * (kUmmaK * 2 >> 4)),
+                                          idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+                        if constexpr (kPair) umma_commit_pair(&empty[stage], 0b11);
+                        else if constexpr (kMcast) umma_commit_mc(&empty[stage], kAllCtas);
+                        else umma_commit(&empty[stage]);
                     }
                     __syncwarp();
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                if (elect_one()) umma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
+                if (elect_one()) {                                // accumulator complete -> epilogue(s)
+                    if constexpr (kPair) umma_commit_pair(&tmem_full[acc], 0b11);
+                    else umma_commit(&tmem_full[acc]);
+                }
                 __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -204,7 +234,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             epi.tile(ep, sched, t_acc, ewarp, lane, epi_smem);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         epi.end(ep, lane);
@@ -217,7 +250,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
     if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if constexpr (kPair) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
