@@ -177,6 +177,18 @@ OFX_API int ofx_topk_search(const void* packed, const float* gallery_f32, int64_
 OFX_API int ofx_topk_merge(const double* scores, const int64_t* idx, int32_t n_lists, int32_t n_query,
                    int32_t k, double* out_score, int64_t* out_idx, void* stream);
 
+/* ---- per-category candidate pools: the retrieval evaluation of
+ * complementary_item_retrieval_trainer.py:192-249 ranks every query against the pool of its target
+ * category only (<= 3000 items, polyvore_complementary_item_retrieval_dataset.py:111-153) with
+ * cdist -> topk(50, largest=False).  pools: all pools concatenated, (total_rows, dim) fp32;
+ * pool_offsets (n_pools + 1) row offsets (device); query_pool (n_query) pool index of each query
+ * (device).  Exact fp64 scores, ties to the lowest index; out_idx (n_query, k) are POOL-LOCAL row
+ * indices (-1 past the pool size), k <= 64, pools of at most 4096 rows. */
+OFX_API int ofx_pool_search(const float* pools, const int64_t* pool_offsets, int32_t n_pools,
+                    int32_t max_pool_rows, const float* queries, const int32_t* query_pool,
+                    int32_t n_query, int32_t dim, int32_t k, int32_t metric, double* out_score,
+                    int64_t* out_idx, void* stream);
+
 /* ---- building block exported for tests / profiling: C = A . W^T (+bias)(+mish)(+residual)
  * A (M,K) bf16 pitch lda, W (N,K) bf16 pitch ldw on the tcgen05 pipeline.  out is bf16 or
  * fp32 (out_f32), pitch ldo; residual fp32 pitch ldr or NULL.  N % 128 == 0, K % 64 == 0. */

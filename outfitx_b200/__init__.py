@@ -9,7 +9,7 @@ from .datatypes import (FashionItem, OutfitCompatibilityPredictionTask,  # noqa:
                         OutfitPrecomputeEmbeddingTask)
 
 __all__ = ["OutfitX", "aggregate_embeddings", "Gallery", "cir_search", "local_search", "merge_lists",
-           "ShardedSearch", "shard_rows", "OutfitXConfig", "TransformerConfig", "ItemEncoderConfig",
+           "ShardedSearch", "shard_rows", "PoolSet", "pool_search", "recall_at_k", "load_embedding_pickles", "OutfitXConfig", "TransformerConfig", "ItemEncoderConfig",
            "OutfitCompatibilityPredictionTask", "OutfitComplementaryItemRetrievalTask",
            "OutfitFillInTheBlankTask", "OutfitPrecomputeEmbeddingTask", "FashionItem"]
 
@@ -18,7 +18,8 @@ def __getattr__(name):  # torch is imported lazily so that `import outfitx_b200.
     if name in ("OutfitX", "aggregate_embeddings"):
         from . import model
         return getattr(model, name)
-    if name in ("Gallery", "cir_search", "local_search", "merge_lists", "ShardedSearch", "shard_rows"):
+    if name in ("Gallery", "cir_search", "local_search", "merge_lists", "ShardedSearch", "shard_rows",
+                "PoolSet", "pool_search", "recall_at_k", "load_embedding_pickles"):
         from . import search
         return getattr(search, name)
     raise AttributeError(name)

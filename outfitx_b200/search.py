@@ -164,3 +164,106 @@ def cir_search(queries, gallery: Gallery, k: int = 10, metric: str = "l2", exact
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         return ShardedSearch(group).search(queries, gallery, k, metric, exact)
     return local_search(queries, gallery, k, metric, exact)
+
+
+# ---------------------------------------------------------------------------------------------
+# Per-category candidate pools + Recall@k
+# ---------------------------------------------------------------------------------------------
+MAX_POOL_ROWS = 4096
+MAX_POOL_K = 64
+
+
+class PoolSet:
+    """The reference's ``candidate_pools`` (one pool of <= 3000 item embeddings per category,
+    ``polyvore_complementary_item_retrieval_dataset.py:111-153``) resident in HBM: all pools
+    concatenated into one ``(total_rows, dim)`` fp32 matrix plus row offsets."""
+
+    def __init__(self, rows: torch.Tensor, offsets: torch.Tensor, sizes):
+        self.rows, self.offsets, self.sizes = rows, offsets, list(sizes)
+
+    @property
+    def n_pools(self) -> int:
+        return len(self.sizes)
+
+    @classmethod
+    def build(cls, pools) -> "PoolSet":
+        """pools: sequence of ``(n_c, dim)`` CUDA fp32 tensors (pool c = category c)."""
+        if len(pools) == 0:
+            raise ValueError("need at least one pool")
+        if any(not p.is_cuda for p in pools):
+            raise RuntimeError("pools must be CUDA tensors: outfitx_b200 has no CPU path")
+        sizes = [int(p.shape[0]) for p in pools]
+        if max(sizes) > MAX_POOL_ROWS or min(sizes) < 1:
+            raise ValueError(f"pools hold 1..{MAX_POOL_ROWS} rows")
+        rows = torch.cat([p.detach().to(torch.float32) for p in pools]).contiguous()
+        off = torch.zeros(len(sizes) + 1, dtype=torch.int64)
+        off[1:] = torch.tensor(sizes, dtype=torch.int64).cumsum(0)
+        return cls(rows, off.to(rows.device), sizes)
+
+
+@torch.no_grad()
+def pool_search(queries: torch.Tensor, query_pool: torch.Tensor, pools: PoolSet, k: int = 50,
+                metric: str = "l2") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k of every query inside ITS pool -> (idx (nq,k) int64 pool-local, -1 past the pool size;
+    score (nq,k) fp64).  Same ranking as ``torch.topk(torch.cdist(q, pool), k, largest=False)``
+    (``complementary_item_retrieval_trainer.py:240-242``), exact, ties to the lowest index."""
+    if metric not in _METRIC:
+        raise ValueError(f"metric must be 'dot' or 'l2', got {metric!r}")
+    if not 1 <= k <= MAX_POOL_K:
+        raise ValueError(f"k must be in [1, {MAX_POOL_K}]")
+    if not queries.is_cuda:
+        raise RuntimeError("queries must be a CUDA tensor: outfitx_b200 has no CPU path")
+    q = queries.detach().to(torch.float32).contiguous()
+    qp = query_pool.to(device=q.device, dtype=torch.int32).contiguous()
+    if q.dim() != 2 or q.shape[1] != pools.rows.shape[1] or qp.shape != (q.shape[0],):
+        raise ValueError("queries must be (nq, dim) and query_pool (nq,)")
+    nq = q.shape[0]
+    if nq and (int(qp.min()) < 0 or int(qp.max()) >= pools.n_pools):
+        raise ValueError("query_pool holds a pool index out of range")
+    idx = torch.empty(nq, k, dtype=torch.int64, device=q.device)
+    score = torch.empty(nq, k, dtype=torch.float64, device=q.device)
+    if nq == 0:
+        return idx, score
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.lib().ofx_pool_search(
+            pools.rows.data_ptr(), pools.offsets.data_ptr(), pools.n_pools, max(pools.sizes), q.data_ptr(),
+            qp.data_ptr(), nq, q.shape[1], k, _METRIC[metric], score.data_ptr(), idx.data_ptr(),
+            torch.cuda.current_stream(q.device).cuda_stream))
+    return idx, score
+
+
+def recall_at_k(topk_idx: torch.Tensor, gt_idx: torch.Tensor, top_k_list=(1, 5, 10, 15, 30, 50)) -> dict:
+    """``Recall@k`` exactly as ``compute_recall_metrics`` scores it
+    (``complementary_item_retrieval_trainer.py:244-249``): the fraction of queries whose
+    ground-truth pool index is among the first k retrieved indices."""
+    gt = gt_idx.to(topk_idx.device).view(-1, 1)
+    out = {}
+    for k in top_k_list:
+        if k > topk_idx.shape[1]:
+            raise ValueError(f"Recall@{k} needs at least {k} retrieved indices")
+        out[f"Recall@{k}"] = float((topk_idx[:, :k] == gt).any(dim=-1).float().mean().item()) if gt.numel() else 0.0
+    return out
+
+
+def load_embedding_pickles(paths, device=None):
+    """The reference's precomputed-embedding wire format: each file is
+    ``pickle.dump({'ids': [int], 'embeddings': np.float32 (N, 2*dim_per_modality)})`` written by
+    ``precompute_embedding_script.py:47-53`` as ``{model_name}_embedding_subset_{rank}.pkl`` and read
+    back by ``compatibility_prediction_trainer.py:329-349`` / ``demo/app.py:51-71``.
+    -> (ids int64 (N,), embeddings fp32 (N, 2*dpm) [on `device` if given], id -> row dict).
+    The text embedding of an item is the second half of its row (``polyvore_item_dataset.py:75``)."""
+    import pickle
+
+    import numpy as np
+    ids, embs = [], []
+    for path in paths:
+        with open(path, "rb") as f:
+            d = pickle.load(f)
+        ids.extend(int(i) for i in d["ids"])
+        embs.append(np.asarray(d["embeddings"], dtype=np.float32))
+    emb = torch.from_numpy(np.concatenate(embs, axis=0))
+    if len(ids) != emb.shape[0]:
+        raise ValueError("ids and embeddings disagree in length")
+    if device is not None:
+        emb = emb.to(device)
+    return torch.tensor(ids, dtype=torch.int64), emb, {i: r for r, i in enumerate(ids)}

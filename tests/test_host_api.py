@@ -71,3 +71,22 @@ def test_shard_rows_partition():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= max(1, w)
+
+
+def test_embedding_pickle_loader(tmp_path):
+    """the reference's precomputed-embedding files (precompute_embedding_script.py:47-53)."""
+    import pickle
+    from outfitx_b200.search import load_embedding_pickles
+    rng = np.random.default_rng(0)
+    paths = []
+    for r, n in enumerate((5, 3)):
+        d = {"ids": [100 * r + i for i in range(n)], "embeddings": rng.standard_normal((n, 1024)).astype(np.float32)}
+        p = tmp_path / f"fashion-clip_embedding_subset_{r}.pkl"
+        with open(p, "wb") as f:
+            pickle.dump(d, f)
+        paths.append(str(p))
+    ids, emb, index = load_embedding_pickles(paths)
+    assert ids.tolist() == [0, 1, 2, 3, 4, 100, 101, 102] and emb.shape == (8, 1024) and emb.dtype == torch.float32
+    assert index[101] == 6
+    text = emb[:, 512:]            # polyvore_item_dataset.py:75: text embedding = second half
+    assert text.shape == (8, 512)
