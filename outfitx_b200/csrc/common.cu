@@ -104,6 +104,24 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
     return OFX_OK;
 }
 
+// 2-D fp32 tensor map: box = box_rows x 32 elements (128 B), 128-byte swizzle
+int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                  uint32_t box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(OFX_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(OFX_E_CUDA, "cuTensorMapEncodeTiled (fp32) failed (%d): rows=%llu cols=%llu ld=%llu",
+                    static_cast<int>(r), (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+    return OFX_OK;
+}
+
 }  // namespace ofx
 
 extern "C" {

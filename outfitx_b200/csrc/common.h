@@ -49,6 +49,10 @@ int sm_count();
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                    uint32_t box_rows);
 
+// 2-D fp32 tensor map, box = box_rows x 32 elements (128 B), 128-byte swizzle
+int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                  uint32_t box_rows);
+
 // CTAs per MMA group in the tcgen05 GEMM / search kernels: 2 = CTA pairs (cta_group::2, default),
 // 1 = independent CTAs (OFX_CLUSTER=1, for A/B timing)
 int cluster_size();

@@ -171,6 +171,7 @@ struct EpiTopK {
     }
 
     __device__ void end(const Params&, int) {}
+    __device__ void pre_tile(const Params&, const SchedSearch&, int, int, uint8_t*) {}
 
     // evict candidate = lowest score, highest index among equal scores.  Static + by-value so
     // the per-thread state stays in registers (no `this` escaping into local memory).

@@ -62,6 +62,8 @@ constexpr int tc_smem_bytes() {
 //   static constexpr int kWarps;   4 or 8 epilogue warps
 //   __device__ void begin(const Params&, const Sched&, int ewarp, int lane, uint8_t* smem);
 //   __device__ void end(const Params&, int lane);   after the last tile (e.g. drain bulk stores)
+//   __device__ void pre_tile(const Params&, const Sched&, int ewarp, int lane, uint8_t* smem);
+//                                   called before waiting for the tile's accumulator
 //   __device__ void tile(const Params&, const Sched&, uint32_t tmem_acc /*lane quarter applied*/,
 //                        int ewarp /*0..kWarps-1: quarter = ewarp & 3, column group = ewarp >> 2*/,
 //                        int lane, uint8_t* epi_smem);
@@ -227,6 +229,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         long long* prof = g_tc_prof;
         long long t0 = clock64(), t_tf = 0, tq;
         while (sched.next()) {
+            epi.pre_tile(ep, sched, ewarp, lane, epi_smem);   // e.g. start fetching the residual tile
             if (prof) { tq = clock64(); mbar_wait(&tmem_full[acc], acc_phase); t_tf += clock64() - tq; }
             else mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
