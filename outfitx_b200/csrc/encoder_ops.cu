@@ -517,20 +517,22 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
     const __nv_bfloat16* gv = static_cast<const __nv_bfloat16*>(a.v);
 
     for (int i = tid; i < STRIDE / 16; i += 128) reinterpret_cast<uint4*>(s_z)[i] = make_uint4(0, 0, 0, 0);
-    const int total = (n_q + 2 * S) * CPR;
-    for (int c = tid; c < total; c += 128) {
-        const int r = c / CPR, cc = c - r * CPR;
-        const __nv_bfloat16* src;
-        uint8_t* dst;
-        int j;
-        if (r < n_q) { j = r; src = gq + static_cast<long long>(j == 0 ? b : base + j - 1) * a.ldq; dst = s_q; }
-        else if (r < n_q + S) { j = r - n_q; src = gk + static_cast<long long>(j == 0 ? b : base + j - 1) * a.ldk; dst = s_k; }
-        else { j = r - n_q - S; src = gv + static_cast<long long>(j == 0 ? b : base + j - 1) * a.ldv; dst = s_v; }
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(
-                         __cvta_generic_to_shared(dst + j * STRIDE + cc * 16))),
-                     "l"(src + cc * 8)
-                     : "memory");
-    }
+    // gather: 16-byte cp.async chunks, (row, chunk) advanced incrementally (no per-chunk division)
+    auto load_rows = [&](const __nv_bfloat16* g, long long ld, uint8_t* dst, int n_rows) {
+        int j = tid / CPR, cc = tid - j * CPR;
+        while (j < n_rows) {
+            const long long row = j == 0 ? b : base + j - 1;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(
+                             __cvta_generic_to_shared(dst + j * STRIDE + cc * 16))),
+                         "l"(g + row * ld + cc * 8)
+                         : "memory");
+            cc += 128;
+            while (cc >= CPR) { cc -= CPR; ++j; }
+        }
+    };
+    load_rows(gk, a.ldk, s_k, S);
+    load_rows(gv, a.ldv, s_v, S);
+    load_rows(gq, a.ldq, s_q, n_q);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -546,6 +548,11 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
     const int a_row = (lane & 7) + 8 * ((lane >> 3) & 1), a_col = 8 * (lane >> 4);     // A operand (q) and V^T
     const int b_row = (lane & 7) + 8 * (lane >> 4), b_col = 8 * ((lane >> 3) & 1);     // B operand (K)
     const float sl2 = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;           // scale * log2(e)
+    uint32_t kvalid = 0;      // bit nt*2+e: key nt*8 + 2*t4 + e exists
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) kvalid |= (nt * 8 + 2 * t4 + e < S ? 1u : 0u) << (nt * 2 + e);
 
 #pragma unroll 1
     for (int hh = 0; hh < 4; ++hh) {
@@ -596,8 +603,7 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
                     for (int nt = 0; nt < 2 * KT; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const int key = nt * 8 + 2 * t4 + e;
-                            float v = key < S && nt < 2 * n_kt ? sc[mt][nt][2 * h + e] * sl2 : -INFINITY;
+                            float v = (kvalid >> (nt * 2 + e)) & 1u ? sc[mt][nt][2 * h + e] * sl2 : -INFINITY;
                             sc[mt][nt][2 * h + e] = v;
                             mx = fmaxf(mx, v);
                         }
