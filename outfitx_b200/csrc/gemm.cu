@@ -40,7 +40,8 @@ struct SchedGemm {
         int bn;
         int cl;            // cluster size: CL consecutive M tiles share one B (weight) tile
     };
-    int m0, n0, m_actual;
+    static constexpr bool kPrefetch = false;
+    int m0, n0, m_actual, pf_n0;
     int tile, step, total, n_tiles, bn, cl, rank;
     __device__ SchedGemm(const Params& p, int cta, int n_cta) {
         m_actual = p.m_dev ? min(*p.m_dev, p.m) : p.m;

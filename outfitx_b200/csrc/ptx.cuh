@@ -84,6 +84,13 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
         "r"(c_inner), "r"(c_outer), "l"(policy)
         : "memory");
 }
+// L2 prefetch of one box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c_inner, int32_t c_outer) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c_inner), "r"(c_outer)
+                 : "memory");
+}
 // Multicast variant: the box lands at the same shared-memory offset in every CTA of `mask`, and
 // complete_tx is signalled on the mbarrier at the same offset in each of them.
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar,

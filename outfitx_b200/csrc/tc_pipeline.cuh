@@ -57,6 +57,7 @@ constexpr int tc_smem_bytes() {
 //   struct Params;  __device__ Sched(const Params&, int cta, int n_cta);
 //   __device__ bool next();          advance to the next tile of this CTA
 //   int m0, n0;                      tile origin (rows of A, rows of B)
+//   static constexpr bool kPrefetch; int pf_n0;   optional: B tile to prefetch into L2 (-1 = none)
 // Epi concept:
 //   struct Params; static constexpr int kSmemBytes;
 //   static constexpr int kWarps;   4 or 8 epilogue warps
@@ -138,6 +139,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             uint32_t phase = 0;
             while (sched.next()) {
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    if constexpr (Sched::kPrefetch) {
+                        // designated CTAs pull a LATER B tile of the sweep into L2 (this CTA's rows of it)
+                        if (sched.pf_n0 >= 0)
+                            tma_prefetch_l2_2d(&tm_b, kb * kBK, sched.pf_n0 + static_cast<int>(crank) * kBRowsPerCta);
+                    }
                     mbar_wait(&empty[stage], phase ^ 1);
                     if constexpr (!kPair) {
                         mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
