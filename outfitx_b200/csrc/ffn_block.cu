@@ -21,8 +21,12 @@
 //   G1(c): acc1[c&1] = H . W1[c]^T          8 k-blocks of 64, N = 256
 //   E (c): U[c&1] = bf16(mish(acc1 + b1))   epilogue warps, TMEM -> smem
 //   G2(c): acc2 += U[c&1] . W2[:, c]^T      4 k-blocks of 64, 2 x (N = 256)
-// issued as G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... so the tensor pipe always has one
-// GEMM phase of work queued while the epilogue of a chunk runs.
+// issued as G1(0) G1(1) | G1(2) G2(0) | G1(3) G2(1) | ... : as soon as E(c) has drained acc1[c&1]
+// the NEXT-BUT-ONE first GEMM goes in front of G2(c), so the epilogue of a chunk has three GEMM
+// phases (~10k cycles) to finish instead of two, and H is released three phases before the tile
+// ends (the LayerNorm prologue of the next tile needs that time).  Because G2(c) is now issued
+// after G1(c+2), "acc1[c&1] is full again" no longer implies "G2(c) has read U[c&1]": E(c+2)
+// waits for an explicit u_free[c&1] commit before it overwrites U.
 //
 // Warp roles (16 warps): 0 TMA producer (weights), 1 MMA issuer (leader CTA only), 2 TMEM
 // allocator, 4-11 epilogue (mish chunks, then the residual epilogue), 12-15 LayerNorm prologue
@@ -101,7 +105,8 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
     uint64_t* w_empty = bars + NSTAGE;          // [NSTAGE]  per CTA (multicast commit)
     uint64_t* acc1_full = bars + 2 * NSTAGE;    // [2]       per CTA (multicast commit)
     uint64_t* u_full = acc1_full + 2;           // [2]       leader's: 16 epilogue-warp arrivals
-    uint64_t* acc2_full = u_full + 2;           //           per CTA (multicast commit)
+    uint64_t* u_free = u_full + 2;              // [2]       per CTA (multicast commit): G2 has read U[b]
+    uint64_t* acc2_full = u_free + 2;           //           per CTA (multicast commit)
     uint64_t* acc2_empty = acc2_full + 1;       //           leader's: 16 arrivals
     uint64_t* h_full = acc2_empty + 1;          //           leader's: 8 LN-warp arrivals
     uint64_t* h_empty = h_full + 1;             //           per CTA (multicast commit)
@@ -127,6 +132,7 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc1_full[i], 1);
             mbar_init(&u_full[i], 2 * N_EPI_WARPS);
+            mbar_init(&u_free[i], 1);
         }
         mbar_init(acc2_full, 1);
         mbar_init(acc2_empty, 2 * N_EPI_WARPS);
@@ -168,8 +174,8 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 g1(0);
                 if (nch > 1) g1(1);
                 for (int c = 0; c < nch; ++c) {
-                    g2(c);
                     if (c + 2 < nch) g1(c + 2);
+                    g2(c);
                 }
             }
         }
@@ -228,10 +234,12 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 }
                 __syncwarp();
             };
-            auto g2 = [&](int c) {
+            auto wait_u = [&](int c) {     // E(c) done: U[c&1] is ready and acc1[c&1] has been drained
                 if (c & 1) { PROF_WAIT(t_u, mbar_wait(&u_full[1], uph1)); uph1 ^= 1; }
                 else       { PROF_WAIT(t_u, mbar_wait(&u_full[0], uph0)); uph0 ^= 1; }
                 tc_fence_after();
+            };
+            auto g2 = [&](int c) {
                 const uint32_t ub = u_lo + (c & 1) * (U_BYTES >> 4);
                 for (int kb = 0; kb < KB2; ++kb) {
                     int ns; uint32_t nph, nready;
@@ -250,6 +258,8 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                     __syncwarp();
                     stage = ns; phase = nph; ready = nready;
                 }
+                if (elect_one()) umma_commit_pair(&u_free[c & 1], 0b11);   // U[c&1] may be overwritten once these retire
+                __syncwarp();
             };
             for (int t = pair; t < n_tiles; t += n_pairs) {
                 PROF_WAIT(t_h, mbar_wait(h_full, tphase));
@@ -257,12 +267,13 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 g1(0);
                 if (nch > 1) g1(1);
                 for (int c = 0; c < nch; ++c) {
+                    wait_u(c);
+                    if (c + 2 < nch) g1(c + 2);
                     if (c == 0) {   // the previous tile's output has left TMEM
                         PROF_WAIT(t_a2, mbar_wait(acc2_empty, tphase ^ 1));
                         tc_fence_after();
                     }
                     g2(c);
-                    if (c + 2 < nch) g1(c + 2);
                 }
                 if (elect_one()) umma_commit_pair(acc2_full, 0b11);
                 __syncwarp();
@@ -290,23 +301,22 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         // staging for the residual epilogue: this warp's own 32-row x 128-byte block of U[0]
         uint8_t* stg = s_u + kblk * KBLK_BYTES + (q & 1) * 4096;
         const int sub_row = lane >> 3, chunk = lane & 7;
-        uint32_t a1ph[2] = {0, 0}, tphase = 0;
+        uint32_t a1ph[2] = {0, 0}, ufph[2] = {1, 1}, tphase = 0;
         for (int t = pair; t < n_tiles; t += n_pairs) {
             for (int c = 0; c < nch; ++c) {
                 const int b = c & 1;
+                // bias of this thread's 64 hidden units (warp-uniform addresses).  With ~224 KB of
+                // shared memory there is next to no L1, so these are L2 round trips: slab 0's are
+                // issued before the barrier wait, slab 1's while slab 0 is being computed.
+                const float4* bias4 = reinterpret_cast<const float4*>(p.b1 + c * CH + nhalf * 128 + ch * 64);
+                float4 bv0[8], bv1[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bv0[i] = __ldg(bias4 + i);
                 mbar_wait(&acc1_full[b], a1ph[b]);
                 a1ph[b] ^= 1;
                 tc_fence_after();
-                const float* bias = p.b1 + c * CH + nhalf * 128 + ch * 64;
                 uint8_t* dst = s_u + b * U_BYTES + u_row;
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    uint32_t raw[32];
-                    tmem_ld_32x32(t_lane + TM_ACC1 + b * 128 + ch * 64 + s * 32, raw);
-                    float4 bv[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + s * 32) + i);
-                    tmem_ld_wait();
+                auto slab = [&](int s, const float4 (&bv)[8], const uint32_t (&raw)[32]) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint32_t w[4];
@@ -323,7 +333,20 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                         }
                         *reinterpret_cast<uint4*>(dst + (((s * 4 + j) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
-                }
+                };
+                uint32_t raw[32];
+                tmem_ld_32x32(t_lane + TM_ACC1 + b * 128 + ch * 64, raw);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bv1[i] = __ldg(bias4 + 8 + i);
+                tmem_ld_wait();
+                // the previous use of U[b] (two chunks ago) must have been read by its G2; the very
+                // first wait on each buffer passes (fresh barrier, parity 1)
+                mbar_wait(&u_free[b], ufph[b]);
+                ufph[b] ^= 1;
+                slab(0, bv0, raw);
+                tmem_ld_32x32(t_lane + TM_ACC1 + b * 128 + ch * 64 + 32, raw);
+                tmem_ld_wait();
+                slab(1, bv1, raw);
                 fence_proxy_async();     // generic-proxy smem writes -> visible to the UMMA (async proxy)
                 tc_fence_before();
                 __syncwarp();
