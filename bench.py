@@ -37,7 +37,7 @@ from outfitx_b200 import synth  # noqa: E402
 
 D_MODEL, D_EMBED, DPM, F_FFN, N_LAYERS = 512, 1024, 512, 2024, 6
 N_CAND, TOPK = 4, 10
-FFN_TRAFFIC_BYTES = 285137152      # dram__bytes_read.sum + dram__bytes_write.sum of one ffn_block_kernel
+FFN_TRAFFIC_BYTES = 293688320      # dram__bytes_read.sum + dram__bytes_write.sum of one ffn_block_kernel
                                    # launch at 82k rows (profiles/r1_ncu_ffn_block.txt)
 
 
