@@ -189,6 +189,29 @@ OFX_API int ofx_pool_search(const float* pools, const int64_t* pool_offsets, int
                     int32_t n_query, int32_t dim, int32_t k, int32_t metric, double* out_score,
                     int64_t* out_idx, void* stream);
 
+/* ---- evaluation-side scoring, forward only.  Scalars come back in fp64 device
+ * memory; reductions are two-stage in a fixed order (deterministic). */
+OFX_API size_t ofx_loss_workspace_bytes(int64_t batch);
+/* FocalLoss.forward (src/losses/focal_loss.py:23-41): logits, labels (n) fp32 (labels as floats, as
+ * the trainer passes them).  per_elem (n) receives the reduction='none' tensor (may be NULL);
+ * out[0] = sum, out[1] = mean.  alpha < 0 skips the alpha_t weighting (focal_loss.py:31). */
+OFX_API int ofx_focal_loss(const float* logits, const float* labels, int64_t n, float gamma, float alpha,
+                   float* per_elem, double* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* SetWiseRankingLoss.forward (src/losses/set_wise_ranking_loss.py:14-37): y, y_hat (B, dim);
+ * negatives (B, n_neg, dim); negative_mask (B, n_neg) bytes, non-zero = padding.
+ * out[0] = L_all + L_hard, out[1] = L_all, out[2] = L_hard. */
+OFX_API int ofx_set_wise_ranking_loss(const float* y, const float* y_hat, const float* negatives,
+                              const uint8_t* negative_mask, int32_t batch, int32_t n_neg,
+                              int32_t dim, float margin, double* out, void* workspace,
+                              size_t workspace_bytes, void* stream);
+/* compute_cp_metrics (src/trains/trainers/compatibility_prediction_trainer.py:406-436):
+ * probs (n) <- sigmoid(logits); counts[0..5] = TP, FP, FN, #correct, #positive, #negative at the
+ * 0.5 threshold; counts[6] = 2 #{pos i, neg j: p_j < p_i} + #{p_j == p_i}, so that
+ * AUC = counts[6] / (2 counts[4] counts[5]) is sklearn's roc_auc_score (ties count 1/2). n <= 2^22. */
+OFX_API int ofx_cp_metrics(const float* logits, const float* labels, int64_t n, float* probs,
+                   int64_t* counts, void* stream);
+
 /* ---- building block exported for tests / profiling: C = A . W^T (+bias)(+mish)(+residual)
  * A (M,K) bf16 pitch lda, W (N,K) bf16 pitch ldw on the tcgen05 pipeline.  out is bf16 or
  * fp32 (out_f32), pitch ldo; residual fp32 pitch ldr or NULL.  N % 128 == 0, K % 64 == 0. */

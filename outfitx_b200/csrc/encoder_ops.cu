@@ -496,10 +496,16 @@ constexpr int kAttnMaxS = 17;
 // BIG = false: this outfit has S <= 16 tokens (one 16-row query tile, one 16-key tile) -- 14 of 15
 // outfits when n ~ U{2..16}; BIG = true adds the second tiles for S = 17.  The kernel picks the
 // body per CTA, so the common case runs straight-line code without per-tile predicates.
-template <int HD, bool BIG>
+//
+// NSPLIT > 1 splits the 16 heads over NSPLIT CTAs (grid.y): each gathers only its DM / NSPLIT columns
+// (still >= 512 contiguous bytes per row), so a CTA needs 1 / NSPLIT of the shared memory and twice
+// as many CTAs are resident per SM -- the kernel is latency-bound (gather -> compute -> store with no
+// overlap inside a CTA), so residency is what hides the gather.
+template <int HD, bool BIG, int NSPLIT>
 __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* sm) {
     constexpr int MT = BIG ? 2 : 1, KT = BIG ? 2 : 1;
-    constexpr int DM = 16 * HD;
+    constexpr int DM = 16 * HD / NSPLIT;     // columns this CTA serves
+    constexpr int HPW = 4 / NSPLIT;          // heads per warp
     constexpr int CPR = DM / 8;              // 16-byte chunks per row
     constexpr int STRIDE = (DM + 8) * 2;     // bytes per shared-memory row
     constexpr int KS = HD / 16;              // k-steps over the head dimension
@@ -512,9 +518,10 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
     const int base = a.batch + a.off[b];
     const int S = min(1 + (a.off[b + 1] - a.off[b]), kAttnMaxS);
     const int n_q = a.row0_only ? 1 : S;
-    const __nv_bfloat16* gq = static_cast<const __nv_bfloat16*>(a.q);
-    const __nv_bfloat16* gk = static_cast<const __nv_bfloat16*>(a.k);
-    const __nv_bfloat16* gv = static_cast<const __nv_bfloat16*>(a.v);
+    const int gcol = NSPLIT > 1 ? static_cast<int>(blockIdx.y) * DM : 0;     // first global column of this CTA
+    const __nv_bfloat16* gq = static_cast<const __nv_bfloat16*>(a.q) + gcol;
+    const __nv_bfloat16* gk = static_cast<const __nv_bfloat16*>(a.k) + gcol;
+    const __nv_bfloat16* gv = static_cast<const __nv_bfloat16*>(a.v) + gcol;
 
     for (int i = tid; i < STRIDE / 16; i += 128) reinterpret_cast<uint4*>(s_z)[i] = make_uint4(0, 0, 0, 0);
     // gather: 16-byte cp.async chunks, (row, chunk) advanced incrementally (no per-chunk division)
@@ -555,8 +562,8 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
         for (int e = 0; e < 2; ++e) kvalid |= (nt * 8 + 2 * t4 + e < S ? 1u : 0u) << (nt * 2 + e);
 
 #pragma unroll 1
-    for (int hh = 0; hh < 4; ++hh) {
-        const int col0 = (warp * 4 + hh) * HD;     // first column of this head
+    for (int hh = 0; hh < HPW; ++hh) {
+        const int col0 = (warp * HPW + hh) * HD;   // first (CTA-local) column of this head
         float sc[MT][2 * KT][4];                          // [query tile][8-key tile][fragment]
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -676,7 +683,7 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
         }
     }
     __syncthreads();
-    __nv_bfloat16* go = static_cast<__nv_bfloat16*>(a.out);
+    __nv_bfloat16* go = static_cast<__nv_bfloat16*>(a.out) + gcol;
     for (int c = tid; c < n_q * CPR; c += 128) {
         const int r = c / CPR, cc = c - r * CPR;
         const long long row = r == 0 ? b : base + r - 1;
@@ -684,26 +691,39 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
     }
 }
 
-template <int HD>
+template <int HD, int NSPLIT>
 __global__ void __launch_bounds__(128)
 attention_mma_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) uint8_t attn_sm[];
     const int b = blockIdx.x;
-    if (a.off[b + 1] - a.off[b] < 16) attention_mma_body<HD, false>(a, attn_sm);   // S = 1 + n <= 16
-    else attention_mma_body<HD, true>(a, attn_sm);
+    if (a.off[b + 1] - a.off[b] < 16) attention_mma_body<HD, false, NSPLIT>(a, attn_sm);   // S = 1 + n <= 16
+    else attention_mma_body<HD, true, NSPLIT>(a, attn_sm);
+}
+
+template <int HD, int NSPLIT>
+static int launch_attention_mma_split(const AttnArgs& a, cudaStream_t stream) {
+    constexpr int smem = (3 * kAttnMaxS + 1) * (16 * HD / NSPLIT + 8) * 2;
+    static bool configured = false;
+    if (!configured) {
+        OFX_CUDA(cudaFuncSetAttribute(attention_mma_kernel<HD, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    attention_mma_kernel<HD, NSPLIT><<<dim3(a.batch, NSPLIT), 128, smem, stream>>>(a);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
 }
 
 template <int HD>
 static int launch_attention_mma(const AttnArgs& a, cudaStream_t stream) {
-    constexpr int smem = (3 * kAttnMaxS + 1) * (16 * HD + 8) * 2;
-    static bool configured = false;
-    if (!configured) {
-        OFX_CUDA(cudaFuncSetAttribute(attention_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+    static int split = -1;   // OFX_ATTN_SPLIT = 1 | 2 | 4 (A/B timing); default 2
+    if (split < 0) {
+        const char* e = getenv("OFX_ATTN_SPLIT");
+        split = e ? atoi(e) : 2;
+        if (split != 1 && split != 2 && split != 4) split = 2;
     }
-    attention_mma_kernel<HD><<<a.batch, 128, smem, stream>>>(a);
-    OFX_LAUNCH_CHECK();
-    return OFX_OK;
+    if (split == 4) return launch_attention_mma_split<HD, 4>(a, stream);
+    if (split == 2) return launch_attention_mma_split<HD, 2>(a, stream);
+    return launch_attention_mma_split<HD, 1>(a, stream);
 }
 
 template <class T>
