@@ -228,6 +228,14 @@ OFX_API int ofx_ffn_block_bf16(float* x, int32_t rows, int32_t d_model, int32_t 
                        const float* ln_w, const float* ln_b, const void* w1, const float* b1,
                        const void* w2, const float* b2, void* stream);
 
+/* Same block, and in the same kernel h_next (rows, d_model) bf16 <- LayerNorm(x_new; next_ln_w,
+ * next_ln_b): norm1 of the FOLLOWING encoder layer (transformer.py:944-947), computed by otherwise idle
+ * warps from the rows the block has just written, so the inter-layer LayerNorm kernel disappears. */
+OFX_API int ofx_ffn_block_ln_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_padded,
+                          const float* ln_w, const float* ln_b, const void* w1, const float* b1,
+                          const void* w2, const float* b2, void* h_next, const float* next_ln_w,
+                          const float* next_ln_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,16 @@ static bool fused_ffn_enabled() {
     return on == 1;
 }
 
+// OFX_FFN_LN=0: separate LayerNorm-1 kernel between layers instead of the FFN block emitting it (A/B timing)
+static bool ffn_emits_ln() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("OFX_FFN_LN");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
 template <class T> static int gemm(const GemmArgs& g, cudaStream_t st);
 template <> int gemm<float>(const GemmArgs& g, cudaStream_t st) { return gemm_f32(g, st); }
 template <> int gemm<__nv_bfloat16>(const GemmArgs& g, cudaStream_t st) { return gemm_bf16(g, st); }
@@ -169,7 +179,9 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
 
     for (int l = 0; l < L.nl; ++l) {
         const bool last = l == L.nl - 1;
-        if (l > 0) OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln1w), lf(l, L.ln1b), h, st));
+        // with the fused FFN block the previous layer has already emitted h = norm1_l(x)
+        if (l > 0 && !(fused_ffn && ffn_emits_ln()))
+            OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln1w), lf(l, L.ln1b), h, st));
         AttnArgs at{};
         at.batch = B; at.n_head = s->n_head; at.off = off; at.max_s = s->max_items + 1;
         at.max_rows = W.t_max; at.n_tok = n_tok; at.owner = owner;
@@ -186,6 +198,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
             if (fused_ffn) {
                 FfnBlockArgs fa{x, W.t_max, n_tok, dm, fp, lf(l, L.ln2w), lf(l, L.ln2b), lw(l, L.w_1),
                                 lf(l, L.b_1), lw(l, L.w_2), lf(l, L.b_2)};
+                if (ffn_emits_ln()) { fa.h_next = h; fa.lnn_w = lf(l + 1, L.ln1w); fa.lnn_b = lf(l + 1, L.ln1b); }
                 OFX_TRY(ffn_block_bf16(fa, st));
             } else {
                 OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
@@ -329,6 +342,21 @@ int ofx_ffn_block_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_pa
         return fail(OFX_E_SHAPE, "ofx_ffn_block_bf16: needs d_model 512 and d_ffn_padded %% 256 == 0");
     OFX_TRY(require_sm100());
     FfnBlockArgs fa{x, rows, nullptr, d_model, d_ffn_padded, ln_w, ln_b, w1, b1, w2, b2};
+    return ffn_block_bf16(fa, static_cast<cudaStream_t>(stream));
+}
+
+int ofx_ffn_block_ln_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_padded, const float* ln_w,
+                          const float* ln_b, const void* w1, const float* b1, const void* w2, const float* b2,
+                          void* h_next, const float* next_ln_w, const float* next_ln_b, void* stream) {
+    if (!x || !ln_w || !ln_b || !w1 || !b1 || !w2 || !b2 || !h_next || !next_ln_w || !next_ln_b)
+        return fail(OFX_E_ARG, "ofx_ffn_block_ln_bf16: null argument");
+    if (rows < 0) return fail(OFX_E_SHAPE, "ofx_ffn_block_ln_bf16: rows %d", rows);
+    if (!ffn_block_supported(d_model, d_ffn_padded))
+        return fail(OFX_E_SHAPE, "ofx_ffn_block_ln_bf16: needs d_model 512 and d_ffn_padded %% 256 == 0");
+    if (reinterpret_cast<uintptr_t>(h_next) % 16) return fail(OFX_E_ARG, "ofx_ffn_block_ln_bf16: misaligned h_next");
+    OFX_TRY(require_sm100());
+    FfnBlockArgs fa{x, rows, nullptr, d_model, d_ffn_padded, ln_w, ln_b, w1, b1, w2, b2};
+    fa.h_next = h_next; fa.lnn_w = next_ln_w; fa.lnn_b = next_ln_b;
     return ffn_block_bf16(fa, static_cast<cudaStream_t>(stream));
 }
 }

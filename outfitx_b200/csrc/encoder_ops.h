@@ -46,6 +46,9 @@ struct FfnBlockArgs {
     const float* b1;       // (fp)
     const void* w2;        // (dm, fp) bf16
     const float* b2;       // (dm)
+    void* h_next = nullptr;        // optional (rows, dm) bf16: LayerNorm (lnn_w, lnn_b) of the updated x,
+    const float* lnn_w = nullptr;  // i.e. norm1 of the next layer, emitted by the same kernel
+    const float* lnn_b = nullptr;
 };
 bool ffn_block_supported(int dm, int fp);
 int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream);

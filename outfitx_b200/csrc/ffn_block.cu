@@ -67,6 +67,9 @@ struct Params {
     const float* b1;        // (n_chunks * 256) fp32, zero beyond d_ffn
     const float* b2;        // (512)
     int n_chunks;           // padded d_ffn / 256
+    __nv_bfloat16* h_next;  // optional (rows, 512) bf16: LayerNorm 1 of the NEXT layer applied to the new x
+    const float* lnn_w;     // its affine terms
+    const float* lnn_b;
     int debug;              // OFX_FFN_DEBUG: 1 = skip mish (timing experiments only)
     long long* prof;        // debug bit 3: per-pair cycle counters of the MMA warp (8 per pair)
 };
@@ -110,7 +113,8 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
     uint64_t* acc2_empty = acc2_full + 1;       //           leader's: 16 arrivals
     uint64_t* h_full = acc2_empty + 1;          //           leader's: 8 LN-warp arrivals
     uint64_t* h_empty = h_full + 1;             //           per CTA (multicast commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + 1);
+    uint64_t* x_done = h_empty + 1;             //           per CTA: 8 epilogue-warp arrivals, new x rows are in global memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_done + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -138,6 +142,7 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         mbar_init(acc2_empty, 2 * N_EPI_WARPS);
         mbar_init(h_full, 2 * N_LN_WARPS);
         mbar_init(h_empty, 1);
+        mbar_init(x_done, N_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
@@ -390,14 +395,71 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 }
             }
             tc_fence_before();
+            __threadfence_block();      // the new x rows (global stores above) before the x_done arrival
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(a2empty);
+            if (lane == 0) {
+                mbar_arrive_cluster(a2empty);
+                if (p.h_next) mbar_arrive(x_done);
+            }
         }
     } else if (warp >= LN_WARP0) {
-        // ------------------------------------------------------------ LayerNorm prologue: x rows -> H
+        // ------------------------------------------------------------ LayerNorm warps
+        // (1) prologue: LN2 of this tile's x rows -> H (bf16, swizzled K-major operand layout);
+        // (2) in the idle time that follows, LN1 of the NEXT layer on the PREVIOUS tile's freshly
+        //     written x rows -> h_next (bf16, row-major), re-read from L2: the separate LayerNorm
+        //     kernel between two layers (one more read of x from HBM) disappears.
         const int lw = warp - LN_WARP0;
         const uint32_t hfull = mapa_shared(smem_u32(h_full), 0);
-        uint32_t tphase = 0;
+        uint32_t tphase = 0, xphase = 0;
+        // two-pass LayerNorm of 4 rows held in registers (lane owns columns i*128 + lane*4 .. +3)
+        auto norm4 = [&](float4 (&v)[4][4], const float* gw, const float* gb, auto&& emit) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s += v[u][i].x + v[u][i].y + v[u][i].z + v[u][i].w;
+                const float mu = warp_sum(s) * (1.f / DM);
+                float qq = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float a = v[u][i].x - mu, b = v[u][i].y - mu, c = v[u][i].z - mu, d = v[u][i].w - mu;
+                    qq += a * a + b * b + c * c + d * d;
+                }
+                const float rstd = rsqrtf(warp_sum(qq) * (1.f / DM) + 1e-5f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gw + i * 128 + lane * 4));
+                    const float4 be = __ldg(reinterpret_cast<const float4*>(gb + i * 128 + lane * 4));
+                    emit(u, i, (v[u][i].x - mu) * rstd * g.x + be.x, (v[u][i].y - mu) * rstd * g.y + be.y,
+                         (v[u][i].z - mu) * rstd * g.z + be.z, (v[u][i].w - mu) * rstd * g.w + be.w);
+                }
+            }
+        };
+        auto ln_next = [&](int t) {      // LN1(next layer) of tile t's new rows -> h_next
+            mbar_wait(x_done, xphase);   // this CTA's epilogue warps have stored them
+            xphase ^= 1;
+            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 16;
+#pragma unroll 1
+            for (int rb = 0; rb < 16; rb += 4) {
+                if (row0 + rb >= n_rows) break;
+                float4 v[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long row = row0 + rb + u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        v[u][i] = row < n_rows ? ldg128(p.x + row * DM + i * 128 + lane * 4)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                norm4(v, p.lnn_w, p.lnn_b, [&](int u, int i, float y0, float y1, float y2, float y3) {
+                    const long long row = row0 + rb + u;
+                    if (row < n_rows)
+                        *reinterpret_cast<uint2*>(p.h_next + row * DM + i * 128 + lane * 4) =
+                            make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+                });
+            }
+        };
+        int prev = -1;
         for (int t = pair; t < n_tiles; t += n_pairs) {
             const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 16;
             // pull this warp's 16 rows (32 KB) towards L2 while the previous tile still owns H
@@ -420,43 +482,24 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                         v[u][i] = row < n_rows ? *reinterpret_cast<const float4*>(p.x + row * DM + i * 128 + lane * 4)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) s += v[u][i].x + v[u][i].y + v[u][i].z + v[u][i].w;
-                    const float mu = warp_sum(s) * (1.f / DM);
-                    float qq = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float a = v[u][i].x - mu, b = v[u][i].y - mu, c = v[u][i].z - mu, d = v[u][i].w - mu;
-                        qq += a * a + b * b + c * c + d * d;
-                    }
-                    const float rstd = rsqrtf(warp_sum(qq) * (1.f / DM) + 1e-5f);
+                norm4(v, p.ln_w, p.ln_b, [&](int u, int i, float y0, float y1, float y2, float y3) {
                     const int r = lw * 16 + rb + u;      // row within this CTA's 64
-                    const bool live = row0 + rb + u < n_rows;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w + i * 128 + lane * 4));
-                        const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln_b + i * 128 + lane * 4));
-                        float y0 = (v[u][i].x - mu) * rstd * g.x + be.x;
-                        float y1 = (v[u][i].y - mu) * rstd * g.y + be.y;
-                        float y2 = (v[u][i].z - mu) * rstd * g.z + be.z;
-                        float y3 = (v[u][i].w - mu) * rstd * g.w + be.w;
-                        if (!live) y0 = y1 = y2 = y3 = 0.f;
-                        // element e = i*128 + lane*4: k-block e/64, 16-byte chunk (e%64)/8, 8-byte half
-                        const int kb = i * 2 + (lane >> 4);
-                        const int c16 = (lane & 15) >> 1;
-                        uint8_t* dst = s_h + kb * KBLK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 +
-                                       ((c16 ^ (r & 7)) << 4) + (lane & 1) * 8;
-                        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
-                    }
-                }
+                    if (row0 + rb + u >= n_rows) y0 = y1 = y2 = y3 = 0.f;
+                    // element e = i*128 + lane*4: k-block e/64, 16-byte chunk (e%64)/8, 8-byte half
+                    const int kb = i * 2 + (lane >> 4);
+                    const int c16 = (lane & 15) >> 1;
+                    uint8_t* dst = s_h + kb * KBLK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 +
+                                   ((c16 ^ (r & 7)) << 4) + (lane & 1) * 8;
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+                });
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(hfull);
+            if (p.h_next && prev >= 0) ln_next(prev);
+            prev = t;
         }
+        if (p.h_next && prev >= 0) ln_next(prev);
     }
     tc_fence_before();
     __syncthreads();
@@ -489,7 +532,9 @@ int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
     const int n_tiles = (a.rows + TILE - 1) / TILE;
     const int max_pairs = sm_count() / 2;
     const int pairs = n_tiles < max_pairs ? n_tiles : max_pairs;
-    Params p{a.x, a.rows, a.rows_dev, a.ln_w, a.ln_b, a.b1, a.b2, a.fp / CH, debug, nullptr};
+    if (a.h_next && (!a.lnn_w || !a.lnn_b)) return fail(OFX_E_ARG, "ffn_block: h_next needs the next layer's LayerNorm terms");
+    Params p{a.x, a.rows, a.rows_dev, a.ln_w, a.ln_b, a.b1, a.b2, a.fp / CH,
+             static_cast<__nv_bfloat16*>(a.h_next), a.lnn_w, a.lnn_b, debug, nullptr};
     static long long* prof_dev = nullptr;
     if (debug & 8) {
         if (!prof_dev) OFX_CUDA(cudaMalloc(&prof_dev, 8 * 8 * 128));

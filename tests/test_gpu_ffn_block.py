@@ -62,3 +62,27 @@ def test_ffn_block_rejects_other_shapes():
     rc = _lib.lib().ofx_ffn_block_bf16(x.data_ptr(), 4, 1024, 2048, x.data_ptr(), x.data_ptr(), x.data_ptr(),
                                        x.data_ptr(), x.data_ptr(), x.data_ptr(), None)
     assert rc == -1
+
+
+@pytest.mark.parametrize("rows", [1, 64, 129, 1000, 128 * 74 + 5, 128 * 74 * 3 + 77])
+def test_ffn_block_emits_next_layer_norm(rows):
+    """ofx_ffn_block_ln_bf16: same x as the plain block, and h_next == bf16(LayerNorm(x_new)) with the next
+    layer's norm1 terms (rows of several tiles per CTA pair exercise the deferred per-tile hand-over)."""
+    from outfitx_b200 import _lib
+    ln_w, ln_b, w1, b1, w2, b2, g = _params(rows + 1)
+    nw = 1.0 + 0.1 * torch.randn(DM, device="cuda", generator=g)
+    nb = 0.1 * torch.randn(DM, device="cuda", generator=g)
+    x = torch.randn(rows, DM, device="cuda", generator=g) * 0.7 + 0.05
+    plain = _run(x, ln_w, ln_b, w1, b1, w2, b2)
+    out = x.clone()
+    h = torch.full((rows + 3, DM), 7.0, device="cuda", dtype=torch.bfloat16)     # 3 guard rows
+    _lib.check(_lib.lib().ofx_ffn_block_ln_bf16(
+        out.data_ptr(), rows, DM, w1.shape[0], ln_w.data_ptr(), ln_b.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+        w2.data_ptr(), b2.data_ptr(), h.data_ptr(), nw.data_ptr(), nb.data_ptr(),
+        torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)
+    want = F.layer_norm(out, (DM,), nw, nb, 1e-5)
+    torch.testing.assert_close(h[:rows].float(), want, rtol=8e-3, atol=2e-5)    # one bf16 rounding
+    assert (h[:rows].float() - want).abs().max() < 0.02 * (1 + want.abs().max())
+    assert bool((h[rows:] == 7.0).all())                                          # nothing past `rows`
