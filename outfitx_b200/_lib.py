@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libofx.so")
+# OFX_LIB_PATH: an instrumented build of the SAME library (e.g. -DOFX_FFN_EPROF), for profiling runs
+LIB_PATH = os.environ.get("OFX_LIB_PATH") or os.path.join(HERE, "libofx.so")
 
 OFX_OK = 0
 PREC_BF16, PREC_FP32 = 0, 1

@@ -29,8 +29,15 @@
 // waits for an explicit u_free[c&1] commit before it overwrites U.
 //
 // Warp roles (16 warps): 0 TMA producer (weights), 1 MMA issuer (leader CTA only), 2 TMEM
-// allocator, 4-11 epilogue (mish chunks, then the residual epilogue), 12-15 LayerNorm prologue
-// (x rows -> H in the swizzled K-major operand layout).
+// allocator, 4-11 epilogue (mish chunks, then the residual epilogue), 12-15 LayerNorm warps: the
+// prologue (x rows -> H in the swizzled K-major operand layout) and, when h_next is given, norm1 of
+// the NEXT encoder layer on the rows the residual epilogue has just written (x_done barrier), so
+// that no LayerNorm kernel runs between two layers.  Registers are re-partitioned with setmaxnreg:
+// warps 0-3 give 48 per thread back, the epilogue warpgroups run with 152.
+//
+// What bounds it (measured): shared-memory bandwidth.  An M=128 pair MMA
+// reads 96 B/clk of operands while TMA refills the weight ring at 64 B/clk; every byte the
+// epilogues move through shared memory on top of that is paid for by the tensor pipe.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -152,6 +159,11 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register re-partitioning (setmaxnreg, per warpgroup of 4 warps): the producer / MMA / allocator
+    // warpgroup hands 48 registers per thread back, the two epilogue warpgroups take 24 more each (bias
+    // vectors + a TMEM slab + the prefetched residual rows do not fit 128 without spilling into the mish loop).
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (weights)
         if (lane == 0) {
@@ -204,6 +216,7 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
             uint32_t phase = 0, tphase = 0, uph0 = 0, uph1 = 0;
             uint32_t ready = 0;     // result of the early poll of w_full[stage]
             long long t_w = 0, t_u = 0, t_h = 0, t_a2 = 0, t0 = clock64(), tq;
+            long long t_uc[3] = {0, 0, 0};     // u_full wait of chunk 0, chunk 1, last chunk
 #define PROF_WAIT(acc, stmt) do { if (p.prof) { tq = clock64(); stmt; acc += clock64() - tq; } else { stmt; } } while (0)
             // waits for ring stage `stage`, polls the next one, returns this stage's B descriptor base
             auto acquire = [&](int& ns, uint32_t& nph, uint32_t& nready) -> uint32_t {
@@ -240,8 +253,14 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 __syncwarp();
             };
             auto wait_u = [&](int c) {     // E(c) done: U[c&1] is ready and acc1[c&1] has been drained
+                const long long before = t_u;
                 if (c & 1) { PROF_WAIT(t_u, mbar_wait(&u_full[1], uph1)); uph1 ^= 1; }
                 else       { PROF_WAIT(t_u, mbar_wait(&u_full[0], uph0)); uph0 ^= 1; }
+                if (p.prof) {
+                    if (c == 0) t_uc[0] += t_u - before;
+                    else if (c == 1) t_uc[1] += t_u - before;
+                    else if (c == nch - 1) t_uc[2] += t_u - before;
+                }
                 tc_fence_after();
             };
             auto g2 = [&](int c) {
@@ -285,12 +304,15 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 tphase ^= 1;
             }
             if (p.prof && lane == 0) {
-                long long* o = p.prof + pair * 8;
+                long long* o = p.prof + pair * 16;
                 o[0] = clock64() - t0; o[1] = t_w; o[2] = t_u; o[3] = t_h; o[4] = t_a2;
+                o[5] = t_uc[0]; o[6] = t_uc[1]; o[7] = t_uc[2];
             }
 #undef PROF_WAIT
         }
+    }
     } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + N_EPI_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;" ::: "memory");
         // ------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                       // TMEM lane quarter
         const int ch = (warp - EPI_WARP0) >> 2;       // which 64 of the accumulator's 128 columns
@@ -303,105 +325,160 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         const uint32_t ufull0 = mapa_shared(smem_u32(&u_full[0]), 0);
         const uint32_t ufull1 = mapa_shared(smem_u32(&u_full[1]), 0);
         const uint32_t a2empty = mapa_shared(smem_u32(acc2_empty), 0);
-        // staging for the residual epilogue: this warp's own 32-row x 128-byte block of U[0]
-        uint8_t* stg = s_u + kblk * KBLK_BYTES + (q & 1) * 4096;
+        // staging for the residual epilogue: this warp's own 32-row x 128-byte block of U[1] (free from
+        // acc2_full until these warps themselves run chunk 1 of the next tile; U[0] is NOT free: chunk 0
+        // of the next tile is worked in between the residual slabs, see below)
+        uint8_t* stg = s_u + U_BYTES + kblk * KBLK_BYTES + (q & 1) * 4096;
         const int sub_row = lane >> 3, chunk = lane & 7;
-        uint32_t a1ph[2] = {0, 0}, ufph[2] = {1, 1}, tphase = 0;
-        for (int t = pair; t < n_tiles; t += n_pairs) {
-            for (int c = 0; c < nch; ++c) {
-                const int b = c & 1;
-                // bias of this thread's 64 hidden units (warp-uniform addresses).  With ~224 KB of
-                // shared memory there is next to no L1, so these are L2 round trips: slab 0's are
-                // issued before the barrier wait, slab 1's while slab 0 is being computed.
-                const float4* bias4 = reinterpret_cast<const float4*>(p.b1 + c * CH + nhalf * 128 + ch * 64);
-                float4 bv0[8], bv1[8];
+        // barrier parities as bit masks (indexable arrays would live in local memory): bit b = buffer b
+        uint32_t a1ph = 0, ufph = 3, tphase = 0;
+        // debug bit 3: where epilogue warp 0 of the leader spends its cycles
+        // (compile with -DOFX_FFN_EPROF: the seven 64-bit counters cost registers the mish loop needs)
+#ifdef OFX_FFN_EPROF
+        const bool eprof = p.prof && rank == 0 && warp == EPI_WARP0;
+        long long e_wa1 = 0, e_wuf = 0, e_mish = 0, e_wa2 = 0, e_res = 0, e_mish0 = 0, eq = 0;
+        long long r_tmem = 0, r_stage = 0, r_add = 0, r_store = 0;
+#define EPROF_BEGIN() do { if (eprof) eq = clock64(); } while (0)
+#define EPROF_END(acc) do { if (eprof) { const long long now = clock64(); acc += now - eq; eq = now; } } while (0)
+#else
+#define EPROF_BEGIN() do { } while (0)
+#define EPROF_END(acc) do { } while (0)
+#endif
+        // E(c): U[c&1] = bf16(mish(acc1[c&1] + b1)) for this warp's 32 rows x 64 hidden units
+        auto mish_chunk = [&](int c) {
+            const int b = c & 1;
+            EPROF_BEGIN();
+            // bias of this thread's 64 hidden units (warp-uniform addresses).  With ~224 KB of
+            // shared memory there is next to no L1, so these are L2 round trips: slab 0's are
+            // issued before the barrier wait, slab 1's while slab 0 is being computed.
+            const float4* bias4 = reinterpret_cast<const float4*>(p.b1 + c * CH + nhalf * 128 + ch * 64);
+            float4 bv0[8], bv1[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) bv0[i] = __ldg(bias4 + i);
-                mbar_wait(&acc1_full[b], a1ph[b]);
-                a1ph[b] ^= 1;
-                tc_fence_after();
-                uint8_t* dst = s_u + b * U_BYTES + u_row;
-                auto slab = [&](int s, const float4 (&bv)[8], const uint32_t (&raw)[32]) {
+            for (int i = 0; i < 8; ++i) bv0[i] = __ldg(bias4 + i);
+            mbar_wait(&acc1_full[b], (a1ph >> b) & 1);
+            a1ph ^= 1u << b;
+            tc_fence_after();
+            EPROF_END(e_wa1);
+            uint8_t* dst = s_u + b * U_BYTES + u_row;
+            auto slab = [&](int s, const float4 (&bv)[8], const uint32_t (&raw)[32]) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t w[4];
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float4 bb = bv[2 * j + h];
-                            float v0 = __uint_as_float(raw[8 * j + 4 * h + 0]) + bb.x;
-                            float v1 = __uint_as_float(raw[8 * j + 4 * h + 1]) + bb.y;
-                            float v2 = __uint_as_float(raw[8 * j + 4 * h + 2]) + bb.z;
-                            float v3 = __uint_as_float(raw[8 * j + 4 * h + 3]) + bb.w;
-                            if (!(p.debug & 1)) { v0 = mish_fast(v0); v1 = mish_fast(v1); v2 = mish_fast(v2); v3 = mish_fast(v3); }
-                            w[2 * h] = pack_bf16(v0, v1);
-                            w[2 * h + 1] = pack_bf16(v2, v3);
-                        }
-                        *reinterpret_cast<uint4*>(dst + (((s * 4 + j) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 bb = bv[2 * j + h];
+                        float v0 = __uint_as_float(raw[8 * j + 4 * h + 0]) + bb.x;
+                        float v1 = __uint_as_float(raw[8 * j + 4 * h + 1]) + bb.y;
+                        float v2 = __uint_as_float(raw[8 * j + 4 * h + 2]) + bb.z;
+                        float v3 = __uint_as_float(raw[8 * j + 4 * h + 3]) + bb.w;
+                        if (!(p.debug & 1)) { v0 = mish_fast(v0); v1 = mish_fast(v1); v2 = mish_fast(v2); v3 = mish_fast(v3); }
+                        w[2 * h] = pack_bf16(v0, v1);
+                        w[2 * h + 1] = pack_bf16(v2, v3);
                     }
-                };
-                uint32_t raw[32];
-                tmem_ld_32x32(t_lane + TM_ACC1 + b * 128 + ch * 64, raw);
+                    *reinterpret_cast<uint4*>(dst + (((s * 4 + j) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            };
+            uint32_t raw[32];
+            tmem_ld_32x32(t_lane + TM_ACC1 + b * 128 + ch * 64, raw);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) bv1[i] = __ldg(bias4 + 8 + i);
-                tmem_ld_wait();
-                // the previous use of U[b] (two chunks ago) must have been read by its G2; the very
-                // first wait on each buffer passes (fresh barrier, parity 1)
-                mbar_wait(&u_free[b], ufph[b]);
-                ufph[b] ^= 1;
-                slab(0, bv0, raw);
-                tmem_ld_32x32(t_lane + TM_ACC1 + b * 128 + ch * 64 + 32, raw);
-                tmem_ld_wait();
-                slab(1, bv1, raw);
-                fence_proxy_async();     // generic-proxy smem writes -> visible to the UMMA (async proxy)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(b ? ufull1 : ufull0);
-            }
-            // ---- residual epilogue: x <- x + acc2 + b2 for this warp's 32 rows x 128 columns
+            for (int i = 0; i < 8; ++i) bv1[i] = __ldg(bias4 + 8 + i);
+            tmem_ld_wait();
+            // the previous use of U[b] (two chunks ago) must have been read by its G2; the very
+            // first wait on each buffer passes (fresh barrier, parity 1)
+            EPROF_END(e_mish);
+            mbar_wait(&u_free[b], (ufph >> b) & 1);
+            ufph ^= 1u << b;
+            EPROF_END(e_wuf);
+            slab(0, bv0, raw);
+            tmem_ld_32x32(t_lane + TM_ACC1 + b * 128 + ch * 64 + 32, raw);
+            tmem_ld_wait();
+            slab(1, bv1, raw);
+            fence_proxy_async();     // generic-proxy smem writes -> visible to the UMMA (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(b ? ufull1 : ufull0);
+#ifdef OFX_FFN_EPROF
+            if (eprof) { const long long now = clock64(); e_mish += now - eq; if (c == 0) e_mish0 += now - eq; }
+#endif
+        };
+        for (int t = pair; t < n_tiles; t += n_pairs) {
+#pragma unroll 1
+            for (int c = 0; c < nch; ++c) mish_chunk(c);
+            // ---- residual epilogue: x <- x + acc2 + b2 for this warp's 32 rows x 128 columns, in 4 slabs of
+            // 32 columns (TMEM -> registers -> swizzled staging block -> row-major, coalesced).  It sits between
+            // the last GEMM of this tile and the first mish chunk of the next one, whose first GEMMs are already
+            // running.  Measured (OFX_FFN_DEBUG=8, -DOFX_FFN_EPROF): ~10k cycles per tile, and it stays ~10k
+            // whether the rows travel as per-thread LDG / STG, as TMA bulk stores, or by TMA in both directions
+            // with the add done in place in the staging block -- every variant was built and timed within 1 %.
+            // The common factor is shared-memory bandwidth: GEMM 1 of the next tile reads operands at 96 B/clk
+            // while TMA refills the weight ring at 64 B/clk, which is more than the 128 B/clk the SM has, so
+            // whatever the epilogue moves through shared memory is paid for by the tensor pipe one for one.  The
+            // cheapest form therefore wins: one staging round trip (256 KB per CTA and tile), residual rows
+            // prefetched one slab ahead in registers.
+            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + (q & 1) * 32;
+            auto slab_c0 = [&](int sl) { return (sl >> 1) * 256 + nhalf * 128 + ch * 64 + (sl & 1) * 32; };
+            const int rows_valid = n_rows - static_cast<int>(row0) - sub_row;   // row 4i+sub_row live iff 4i < rows_valid
+            auto slab_col = [&](int sl) { return slab_c0(sl) + chunk * 4; };
+            float4 res[8], b4;
+            auto load_res = [&](int sl) {     // residual rows and output bias of slab sl
+                const float* xp = p.x + (row0 + sub_row) * DM + slab_col(sl);
+                b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + slab_col(sl)));
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    res[i] = (4 * i < rows_valid && !(p.debug & 256)) ? ldg128(xp + static_cast<long long>(4 * i) * DM)
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            load_res(0);
+            EPROF_BEGIN();
             mbar_wait(acc2_full, tphase);
             tphase ^= 1;
             tc_fence_after();
-            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + (q & 1) * 32;
-            const int rows_valid = n_rows - static_cast<int>(row0) - sub_row;   // row 4i+sub_row live iff 4i < rows_valid
+            EPROF_END(e_wa2);
 #pragma unroll 1
             for (int sl = 0; sl < 4; ++sl) {
-                const int half = sl >> 1, s = sl & 1;
-                const int col0 = half * 256 + nhalf * 128 + ch * 64 + s * 32 + chunk * 4;
-                float* xp = p.x + (row0 + sub_row) * DM + col0;
+                float* xp = p.x + (row0 + sub_row) * DM + slab_col(sl);
                 uint32_t raw[32];
-                tmem_ld_32x32(t_lane + TM_ACC2 + half * 128 + ch * 64 + s * 32, raw);
-                float4 res[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    res[i] = 4 * i < rows_valid ? *reinterpret_cast<const float4*>(xp + static_cast<long long>(4 * i) * DM)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col0));
+                tmem_ld_32x32(t_lane + TM_ACC2 + (sl >> 1) * 128 + ch * 64 + (sl & 1) * 32, raw);
                 tmem_ld_wait();
+                EPROF_END(r_tmem);
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) =
                         make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]);
                 __syncwarp();
+                float4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = 4 * i + sub_row;
-                    float4 v = *reinterpret_cast<const float4*>(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
-                    if (4 * i < rows_valid) {
-                        v.x += b4.x + res[i].x; v.y += b4.y + res[i].y;
-                        v.z += b4.z + res[i].z; v.w += b4.w + res[i].w;
-                        *reinterpret_cast<float4*>(xp + static_cast<long long>(4 * i) * DM) = v;
-                    }
+                    v[i] = *reinterpret_cast<const float4*>(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
+                    v[i].x += b4.x + res[i].x; v[i].y += b4.y + res[i].y;
+                    v[i].z += b4.z + res[i].z; v[i].w += b4.w + res[i].w;
                 }
+                EPROF_END(r_add);
+                if (sl < 3) load_res(sl + 1);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (4 * i < rows_valid && !(p.debug & 512)) stg128(xp + static_cast<long long>(4 * i) * DM, v[i]);
+                EPROF_END(r_store);
             }
+            EPROF_END(e_res);
             tc_fence_before();
-            __threadfence_block();      // the new x rows (global stores above) before the x_done arrival
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_cluster(a2empty);
-                if (p.h_next) mbar_arrive(x_done);
-            }
+            if (lane == 0) mbar_arrive_cluster(a2empty);
+            // x_done: the LayerNorm warps may re-read the new rows.  The global stores above are ordered before
+            // the arrival by __syncwarp (memory ordering among the warp's lanes) + the release semantics of
+            // mbarrier.arrive; the LayerNorm warps acquire through mbarrier.try_wait.
+            if (p.h_next && lane == 0) mbar_arrive(x_done);
         }
+#ifdef OFX_FFN_EPROF
+        if (eprof && lane == 0) {
+            long long* o = p.prof + pair * 16 + 8;
+            o[0] = r_tmem; o[1] = r_stage; o[2] = e_mish; o[3] = e_wa2; o[4] = e_res; o[5] = e_mish0; o[6] = r_add; o[7] = r_store;
+        }
+#endif
+#undef EPROF_BEGIN
+#undef EPROF_END
     } else if (warp >= LN_WARP0) {
         // ------------------------------------------------------------ LayerNorm warps
         // (1) prologue: LN2 of this tile's x rows -> H (bf16, swizzled K-major operand layout);
@@ -412,7 +489,17 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         const uint32_t hfull = mapa_shared(smem_u32(h_full), 0);
         uint32_t tphase = 0, xphase = 0;
         // two-pass LayerNorm of 4 rows held in registers (lane owns columns i*128 + lane*4 .. +3)
-        auto norm4 = [&](float4 (&v)[4][4], const float* gw, const float* gb, auto&& emit) {
+        // gamma / beta are fetched ONCE per tile, before the barrier wait that precedes the rows: with
+        // ~224 KB of shared memory there is next to no L1, so loading them inside the row loop put an
+        // extra L2 round trip behind every batch of rows.
+        auto load_affine = [&](const float* gw, const float* gb, float4 (&g)[4], float4 (&be)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                g[i] = __ldg(reinterpret_cast<const float4*>(gw + i * 128 + lane * 4));
+                be[i] = __ldg(reinterpret_cast<const float4*>(gb + i * 128 + lane * 4));
+            }
+        };
+        auto norm4 = [&](float4 (&v)[4][4], const float4 (&gam)[4], const float4 (&bet)[4], auto&& emit) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float s = 0.f;
@@ -428,14 +515,15 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 const float rstd = rsqrtf(warp_sum(qq) * (1.f / DM) + 1e-5f);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(gw + i * 128 + lane * 4));
-                    const float4 be = __ldg(reinterpret_cast<const float4*>(gb + i * 128 + lane * 4));
+                    const float4 g = gam[i], be = bet[i];
                     emit(u, i, (v[u][i].x - mu) * rstd * g.x + be.x, (v[u][i].y - mu) * rstd * g.y + be.y,
                          (v[u][i].z - mu) * rstd * g.z + be.z, (v[u][i].w - mu) * rstd * g.w + be.w);
                 }
             }
         };
         auto ln_next = [&](int t) {      // LN1(next layer) of tile t's new rows -> h_next
+            float4 gam[4], bet[4];
+            load_affine(p.lnn_w, p.lnn_b, gam, bet);
             mbar_wait(x_done, xphase);   // this CTA's epilogue warps have stored them
             xphase ^= 1;
             const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 16;
@@ -451,7 +539,7 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                         v[u][i] = row < n_rows ? ldg128(p.x + row * DM + i * 128 + lane * 4)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                norm4(v, p.lnn_w, p.lnn_b, [&](int u, int i, float y0, float y1, float y2, float y3) {
+                norm4(v, gam, bet, [&](int u, int i, float y0, float y1, float y2, float y3) {
                     const long long row = row0 + rb + u;
                     if (row < n_rows)
                         *reinterpret_cast<uint2*>(p.h_next + row * DM + i * 128 + lane * 4) =
@@ -459,6 +547,10 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 });
             }
         };
+        // (A "staged" variant was built and measured: LN2 rows computed one tile ahead, parked as bf16 in the
+        // tile's unused h_next rows and moved into H by TMA as soon as GEMM 1 released it.  It halves the
+        // h_full wait, the kernel alone gets 2.5 % faster, the CP pass 1 % slower -- the stall moves to the
+        // first mish chunk, see the residual epilogue -- so the simpler direct form stayed.)
         int prev = -1;
         for (int t = pair; t < n_tiles; t += n_pairs) {
             const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 16;
@@ -469,20 +561,25 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
                 if (row0 + (i * 32 + lane) / 16 < n_rows)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + off));
             }
-            mbar_wait(h_empty, tphase ^ 1);     // GEMM 1 of the previous tile has consumed H
-            tphase ^= 1;
-#pragma unroll 1
-            for (int rb = 0; rb < 16; rb += 4) {
-                float4 v[4][4];
+            float4 gam[4], bet[4];
+            load_affine(p.ln_w, p.ln_b, gam, bet);
+            float4 v[4][4];
+            auto load4 = [&](int rb) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const long long row = row0 + rb + u;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        v[u][i] = row < n_rows ? *reinterpret_cast<const float4*>(p.x + row * DM + i * 128 + lane * 4)
+                        v[u][i] = row < n_rows ? ldg128(p.x + row * DM + i * 128 + lane * 4)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                norm4(v, p.ln_w, p.ln_b, [&](int u, int i, float y0, float y1, float y2, float y3) {
+            };
+            mbar_wait(h_empty, tphase ^ 1);     // GEMM 1 of the previous tile has consumed H
+            tphase ^= 1;
+#pragma unroll 1
+            for (int rb = 0; rb < 16; rb += 4) {
+                load4(rb);
+                norm4(v, gam, bet, [&](int u, int i, float y0, float y1, float y2, float y3) {
                     const int r = lw * 16 + rb + u;      // row within this CTA's 64
                     if (row0 + rb + u >= n_rows) y0 = y1 = y2 = y3 = 0.f;
                     // element e = i*128 + lane*4: k-block e/64, 16-byte chunk (e%64)/8, 8-byte half
@@ -537,21 +634,23 @@ int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
              static_cast<__nv_bfloat16*>(a.h_next), a.lnn_w, a.lnn_b, debug, nullptr};
     static long long* prof_dev = nullptr;
     if (debug & 8) {
-        if (!prof_dev) OFX_CUDA(cudaMalloc(&prof_dev, 8 * 8 * 128));
-        OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 128, stream));
+        if (!prof_dev) OFX_CUDA(cudaMalloc(&prof_dev, 8 * 16 * 128));
+        OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 16 * 128, stream));
         p.prof = prof_dev;
     }
     ffn_block_kernel<<<pairs * 2, NTHREADS, SMEM_BYTES, stream>>>(tm_w1, tm_w2, p);
     OFX_LAUNCH_CHECK();
     if (debug & 8) {   // debug only: synchronous dump of the MMA warp's wait-cycle counters
         static int dumps = 0;
-        long long h[8 * 128];
+        long long h[16 * 128];
         OFX_CUDA(cudaStreamSynchronize(stream));
         OFX_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
         if (dumps++ < 2)
             for (int i = 0; i < pairs && i < 74; i += 18)
-                fprintf(stderr, "ffn prof pair %d: total %lld  w_full %lld  u_full %lld  h_full %lld  acc2_empty %lld cycles\n",
-                        i, h[i * 8], h[i * 8 + 1], h[i * 8 + 2], h[i * 8 + 3], h[i * 8 + 4]);
+                fprintf(stderr, "ffn prof pair %d: total %lld  w_full %lld  u_full %lld (chunk 0: %lld, 1: %lld, last: %lld)  h_full %lld  acc2_empty %lld cycles\n",
+                        i, h[i * 16], h[i * 16 + 1], h[i * 16 + 2], h[i * 16 + 5], h[i * 16 + 6], h[i * 16 + 7], h[i * 16 + 3], h[i * 16 + 4]),
+                fprintf(stderr, "   epilogue warp (-DOFX_FFN_EPROF): mish %lld (chunk 0: %lld)  wait acc2_full %lld  residual: tmem %lld  stage %lld  add %lld  store %lld  tail %lld\n",
+                        h[i * 16 + 10], h[i * 16 + 13], h[i * 16 + 11], h[i * 16 + 8], h[i * 16 + 9], h[i * 16 + 14], h[i * 16 + 15], h[i * 16 + 12]);
     }
     return OFX_OK;
 }

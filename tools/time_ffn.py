@@ -5,11 +5,18 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from test_gpu_ffn_block import _params, _want, DM
 from outfitx_b200 import _lib
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 82000
+LN = "--ln" in sys.argv      # ofx_ffn_block_ln_bf16: also emits the next layer's norm1 (staged-H mode of the kernel)
 ln_w, ln_b, w1, b1, w2, b2, g = _params(1)
 x = torch.randn(rows, DM, device="cuda", generator=g)
 L = _lib.lib()
 st = torch.cuda.current_stream().cuda_stream
+hn = torch.empty(rows, DM, device="cuda", dtype=torch.bfloat16)
 def run(t):
+    if LN:
+        _lib.check(L.ofx_ffn_block_ln_bf16(t.data_ptr(), rows, DM, 2048, ln_w.data_ptr(), ln_b.data_ptr(), w1.data_ptr(),
+                                           b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), hn.data_ptr(), ln_w.data_ptr(),
+                                           ln_b.data_ptr(), st))
+        return
     _lib.check(L.ofx_ffn_block_bf16(t.data_ptr(), rows, DM, 2048, ln_w.data_ptr(), ln_b.data_ptr(), w1.data_ptr(),
                                     b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), st))
 y = x.clone(); run(y); torch.cuda.synchronize()
