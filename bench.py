@@ -37,8 +37,8 @@ from outfitx_b200 import synth  # noqa: E402
 
 D_MODEL, D_EMBED, DPM, F_FFN, N_LAYERS = 512, 1024, 512, 2024, 6
 N_CAND, TOPK = 4, 10
-FFN_TRAFFIC_BYTES = 293688320      # dram__bytes_read.sum + dram__bytes_write.sum of one ffn_block_kernel
-                                   # launch at 82k rows (profiles/r1_ncu_ffn_block.txt)
+FFN_TRAFFIC_BYTES = 380563456      # dram__bytes_read.sum + dram__bytes_write.sum of one ffn_block_kernel
+                                   # launch (LN-emitting form) at 82158 rows (profiles/r1_ncu_ffn_block_ln.txt)
 
 
 def peaks():
@@ -145,9 +145,11 @@ def timed(fn, steps, warmup, dist_ok, dev, sampler=None):
 
 
 def time_ffn_block(L, rows, dev, reps=20):
-    """ofx_ffn_block_bf16 on `rows` token rows (d_model 512, d_ffn 2024 padded to 2048), inputs rotated
-    over 4 buffers (4 x rows x 2 KB > L2).  Algorithmic flops = 4 * rows * 512 * 2024 (the padded
-    columns are not counted); algorithmic HBM bytes = rows * 4 KB (fp32 row in, fp32 row out)."""
+    """ofx_ffn_block_ln_bf16 -- the form layers 0-4 of the step launch: the fused FFN block that also emits
+    norm1 of the next layer -- on `rows` token rows (d_model 512, d_ffn 2024 padded to 2048), inputs rotated
+    over 4 buffers (4 x rows x 2 KB > L2).  Algorithmic flops = 4 * rows * 512 * 2024 (the padded columns and
+    the LayerNorms are not counted); algorithmic HBM bytes = rows * 5 KB (fp32 row in, fp32 row out, bf16
+    LayerNorm row out)."""
     from outfitx_b200 import _lib
     g = torch.Generator(device=dev).manual_seed(11)
     r = lambda *s: torch.randn(*s, device=dev, generator=g)
@@ -160,9 +162,12 @@ def time_ffn_block(L, rows, dev, reps=20):
     bufs = [r(rows, D_MODEL) for _ in range(4)]
     st = torch.cuda.current_stream(dev).cuda_stream
 
+    h_next = torch.empty(rows, D_MODEL, device=dev, dtype=torch.bfloat16)
+
     def run(x):
-        _lib.check(L.ofx_ffn_block_bf16(x.data_ptr(), rows, D_MODEL, 2048, ln_w.data_ptr(), ln_b.data_ptr(),
-                                        w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), st))
+        _lib.check(L.ofx_ffn_block_ln_bf16(x.data_ptr(), rows, D_MODEL, 2048, ln_w.data_ptr(), ln_b.data_ptr(),
+                                           w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                           h_next.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), st))
     for x in bufs:
         run(x)
     torch.cuda.synchronize(dev)
@@ -468,11 +473,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["burst"], "unit": "TFLOP/s",
                          "frac": dom["tflops"] / pk["burst"], "traffic": FFN_TRAFFIC_BYTES,
-                         "kernel": "ffn_block_kernel (fused LN2 + linear1 + mish + linear2 + residual; dominant "
-                                   "kernel of the step), timed alone with CUDA events",
+                         "kernel": "ffn_block_kernel (fused LN2 + linear1 + mish + linear2 + residual + norm1 of the "
+                                   "next layer; dominant kernel of the step), timed alone with CUDA events",
                          "rows_per_launch": dom["rows"], "us_per_launch": dom["us_per_launch"],
                          "flops_per_launch": dom["flops_per_launch"],
-                         "algorithmic_bytes_per_launch": dom["rows"] * 4096,
+                         "algorithmic_bytes_per_launch": dom["rows"] * 5120,
                          "peak_kind": f"burst bf16, {pk['source']}",
                          "traffic_note": "dram read+write of one launch at 82k rows from profiles/ (ncu --set full)"},
             "roofline_step": {"bound": "tensor", "achieved": cp_tflops, "peak": pk["burst"], "unit": "TFLOP/s",
