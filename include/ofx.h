@@ -148,6 +148,16 @@ typedef struct ofx_forward_args {
     int64_t n_cand_rows;
 } ofx_forward_args;
 
+/* ---- host -> device transfer of a collated batch, valid slots only.  The reference copies the padded
+ * (B, max_items, dpm) tensors whole (`v.to(local_rank)`, compatibility_prediction_trainer.py:140-145);
+ * here the SMs read the PINNED host tensors host_img / host_txt directly (unified addressing) and copy only
+ * the slots whose mask byte is 0 into dev_img / dev_txt (same layout; padded slots are left untouched --
+ * ofx_encoder_forward never reads them).  mask is a DEVICE pointer.  Fails with OFX_E_ARG on pageable
+ * host memory. */
+OFX_API int ofx_fetch_valid_items(const float* host_img, const float* host_txt, const uint8_t* mask,
+                          int32_t batch, int32_t max_items, int32_t dpm, float* dev_img,
+                          float* dev_txt, void* stream);
+
 OFX_API size_t ofx_encoder_workspace_bytes(const ofx_shape* shape, int32_t batch);
 OFX_API int ofx_encoder_forward(const ofx_shape* shape, const void* packed_weights,
                         const ofx_forward_args* args, void* workspace, size_t workspace_bytes,

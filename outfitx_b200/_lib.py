@@ -59,6 +59,8 @@ _SIGNATURES = {
     "ofx_pack_weights": (C.c_int, [C.POINTER(Shape), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "ofx_fuse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                            C.c_void_p, C.c_void_p]),
+    "ofx_fetch_valid_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "ofx_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(Shape), C.c_int32]),
     "ofx_encoder_forward": (C.c_int, [C.POINTER(Shape), C.c_void_p, C.POINTER(ForwardArgs),
                                       C.c_void_p, C.c_size_t, C.c_void_p]),

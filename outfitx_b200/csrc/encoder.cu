@@ -324,6 +324,28 @@ int ofx_fuse(const float* img, const float* txt, int64_t rows, int32_t dpm, int3
     return fuse_rows(img, txt, rows, dpm, mode, normalize, out, static_cast<cudaStream_t>(stream));
 }
 
+int ofx_fetch_valid_items(const float* host_img, const float* host_txt, const uint8_t* mask, int32_t batch,
+                          int32_t max_items, int32_t dpm, float* dev_img, float* dev_txt, void* stream) {
+    if (batch < 0 || max_items < 1) return fail(OFX_E_SHAPE, "ofx_fetch_valid_items: batch %d, max_items %d", batch, max_items);
+    if (dpm < 4 || dpm % 4) return fail(OFX_E_SHAPE, "ofx_fetch_valid_items: dim_per_modality %d must be a multiple of 4", dpm);
+    if (batch == 0) return OFX_OK;
+    if (!host_img || !host_txt || !mask || !dev_img || !dev_txt) return fail(OFX_E_ARG, "ofx_fetch_valid_items: null argument");
+    if ((reinterpret_cast<uintptr_t>(host_img) | reinterpret_cast<uintptr_t>(host_txt) |
+         reinterpret_cast<uintptr_t>(dev_img) | reinterpret_cast<uintptr_t>(dev_txt)) % 16)
+        return fail(OFX_E_ARG, "ofx_fetch_valid_items: misaligned pointer");
+    OFX_TRY(require_sm100());
+    // the source must be page-locked host memory (or device memory): pageable memory is not addressable by the SMs
+    for (const float* ptr : {host_img, host_txt}) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess || at.type == cudaMemoryTypeUnregistered) {
+            cudaGetLastError();
+            return fail(OFX_E_ARG, "ofx_fetch_valid_items: source is not pinned host memory (use tensor.pin_memory())");
+        }
+    }
+    return fetch_valid(host_img, host_txt, mask, static_cast<long long>(batch) * max_items, dpm, dev_img, dev_txt,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int32_t m, int32_t n, int32_t k,
                   const float* bias, int32_t act_mish, const float* residual, int64_t ldr, void* out,
                   int64_t ldo, int32_t out_f32, void* stream) {

@@ -53,6 +53,8 @@ struct FfnBlockArgs {
 bool ffn_block_supported(int dm, int fp);
 int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream);
 
+int fetch_valid(const float* h_img, const float* h_txt, const uint8_t* mask, long long n_slots, int dpm,
+                float* d_img, float* d_txt, cudaStream_t stream);
 int scan_valid(const uint8_t* mask, int batch, int max_items, int* off, int* n_tok, cudaStream_t stream);
 int fuse_rows(const float* img, const float* txt, long long rows, int dpm, int mode, int normalize,
               float* out, cudaStream_t stream);
