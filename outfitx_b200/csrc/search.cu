@@ -660,8 +660,13 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
         // of the gallery).  The main sweep's first round of units then starts at the ~1 % quantile
         // instead of cold, which removes most of the divergent list insertions that dominate on
         // small shards (1 M rows: 19.5 -> see profiles); its candidate lists are overwritten.
-        constexpr long long kWarmRows = 4096;
-        if (W.kcap == 32 && n_rows >= 16 * kWarmRows) {
+        static long long kWarmRows = -1;     // OFX_WARM_ROWS (multiple of 256; 0 = no warm-up), default 4096
+        if (kWarmRows < 0) {
+            const char* e = getenv("OFX_WARM_ROWS");
+            kWarmRows = e ? atoll(e) : 4096;
+            if (kWarmRows % 256) kWarmRows = 4096;
+        }
+        if (W.kcap == 32 && kWarmRows > 0 && n_rows >= 16 * kWarmRows) {
             SearchPlan wp = make_plan(kWarmRows, n_query, sm_count());
             if (wp.cl == W.plan.cl && wp.n_units <= W.plan.n_units) {
                 EpiTopK<32>::Params ep{kWarmRows, n_query, thr, cand_s, cand_i, cand_n};
