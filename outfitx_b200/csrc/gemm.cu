@@ -33,6 +33,8 @@ __device__ __forceinline__ float mish_precise(float x) {
 // tcgen05 path
 // -------------------------------------------------------------------------------------
 struct SchedGemm {
+    static constexpr bool kThrottle = false;
+    __device__ void throttle() {}
     struct Params {
         int m;             // host-side row count (upper bound when m_dev != nullptr)
         const int* m_dev;  // optional device-side row count (token count after compaction)

@@ -56,8 +56,60 @@ struct SchedSearch {
     struct Params {
         int n_qgroups, n_tiles, seg_tiles, n_units, sub_tiles, cl;
         int pf_dist;   // > 0: in-order sweep, query group 0 of every segment prefetches the tile pf_dist ahead into L2
+        int* progress; // [n_units] tile index each unit's producer has reached (-1 not started, huge = done), or null
+        int window;    // a unit may run at most `window` tiles ahead of the slowest co-scheduled unit of its segment
+        int check;     // pacing check every `check` tiles (power of two)
     };
     static constexpr bool kPrefetch = true;
+    static constexpr bool kThrottle = true;
+    // Pacing (producer thread only).  The query groups that sweep the same gallery segment share its tiles
+    // through L2: whoever touches a tile first pulls it from HBM, the others hit.  Nothing keeps them together,
+    // though, and measured at 10 M rows the main sweep read 316 GB from HBM for a 21.8 GB gallery (L2 hit rate
+    // 72 %): the units drift further apart than L2 holds.  Every unit publishes the tile it has reached; every
+    // `check`-th tile a unit waits until it is at most `window` tiles ahead of the slowest unit that was launched in
+    // the same round of the same segment.  The slowest unit never waits, so this cannot deadlock.
+    __device__ void throttle() {
+        if (!p.progress) return;
+        volatile int* pr = p.progress;
+        if (rank == 0) pr[unit] = last ? 0x3fffffff : it;
+        if ((it & (p.check - 1)) != 0 || it == 0 || last) return;
+        const int seg = unit / p.n_qgroups, round = unit / step;
+        const int base = seg * p.n_qgroups;
+        for (;;) {
+            int mn = 0x7fffffff;
+            if ((p.n_qgroups & 3) == 0) {      // 16-byte loads, all in flight before the first use
+                int4 v[16];
+                const int n4 = min(p.n_qgroups >> 2, 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < n4)
+                        asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(p.progress + base + 4 * j));
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j < n4) {
+                        const int e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if ((base + 4 * j + u) / step == round && e[u] >= 0 && e[u] < mn) mn = e[u];
+                    }
+                }
+                for (int g = 64; g < p.n_qgroups; ++g) {
+                    if ((base + g) / step != round) continue;
+                    const int x = pr[base + g];
+                    if (x >= 0 && x < mn) mn = x;
+                }
+            } else {
+                for (int g = 0; g < p.n_qgroups; ++g) {
+                    if ((base + g) / step != round) continue;
+                    const int x = pr[base + g];
+                    if (x >= 0 && x < mn) mn = x;
+                }
+            }
+            if (it - mn <= p.window) break;
+            __nanosleep(200);
+        }
+    }
     int pf_n0;
     int m0, n0, unit, step, rank;
     int seg_lo, seg_len, it, qg;
@@ -165,6 +217,7 @@ struct EpiTopK {
         float* cand_s;             // [n_units][cl][128][KCAP]
         int* cand_i;               // [n_units][128][KCAP] shard-local row ids
         int* cand_n;               // [n_units][128]
+        int* progress;             // [n_units] scheduler pacing state (see SchedSearch::throttle), not used by the epilogue
     };
     static constexpr int kSmemBytes = KCAP * 128 * 8;
     static constexpr int kWarps = 4;
@@ -504,7 +557,7 @@ static PackedGallery gallery_layout(long long n_rows, int dim) {
 }
 
 struct SearchWs {
-    size_t q_bf16, thr, cand_n, cand_s, cand_i, total;
+    size_t q_bf16, thr, cand_n, cand_s, cand_i, prog, total;
     int kcap;
     SearchPlan plan;
 };
@@ -522,6 +575,7 @@ static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     w.cand_n = take(slots * 4);
     w.cand_s = take(slots * w.kcap * 4);
     w.cand_i = take(slots * w.kcap * 4);
+    w.prog = take(static_cast<size_t>(w.plan.n_units) * 4);
     w.total = o;
     return w;
 }
@@ -546,7 +600,13 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     // default: in-order sweep with group 0 prefetching 8 tiles ahead (33 GB instead of 43 GB of DRAM reads at
     // 2 M rows, +1.5 % throughput); OFX_SEARCH_PREFETCH=0 selects the rotated sub-block sweep
     if (pf_dist < 0) { const char* e = getenv("OFX_SEARCH_PREFETCH"); pf_dist = e ? atoi(e) : 8; }
-    SchedSearch::Params sp{pl.n_qgroups, pl.n_tiles, pl.seg_tiles, pl.n_units, pl.sub_tiles, CL, pf_dist};
+    static int window = -1;     // OFX_SEARCH_WINDOW: pacing window in tiles (0 = off)
+    if (window < 0) { const char* e = getenv("OFX_SEARCH_WINDOW"); window = e ? atoi(e) : 8; }
+    int* progress = (window > 0 && pf_dist > 0) ? ep.progress : nullptr;
+    if (progress) OFX_CUDA(cudaMemsetAsync(progress, 0xFF, static_cast<size_t>(pl.n_units) * 4, stream));
+    static int check = -1;      // OFX_SEARCH_CHECK: tiles between pacing checks (power of two)
+    if (check < 0) { const char* e = getenv("OFX_SEARCH_CHECK"); check = e ? atoi(e) : 8; if (check < 1 || (check & (check - 1))) check = 8; }
+    SchedSearch::Params sp{pl.n_qgroups, pl.n_tiles, pl.seg_tiles, pl.n_units, pl.sub_tiles, CL, pf_dist, progress, window, check};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pl.grid);
     cfg.blockDim = dim3(tc_threads<Epi>());
@@ -648,6 +708,7 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
     int* cand_n = reinterpret_cast<int*>(ws + W.cand_n);
     float* cand_s = reinterpret_cast<float*>(ws + W.cand_s);
     int* cand_i = reinterpret_cast<int*>(ws + W.cand_i);
+    int* prog = reinterpret_cast<int*>(ws + W.prog);
 
     if (n_rows > 0) {
         const long long nq_el = static_cast<long long>(n_query) * (dim + kAugCols);
@@ -669,15 +730,15 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
         if (W.kcap == 32 && kWarmRows > 0 && n_rows >= 16 * kWarmRows) {
             SearchPlan wp = make_plan(kWarmRows, n_query, sm_count());
             if (wp.cl == W.plan.cl && wp.n_units <= W.plan.n_units) {
-                EpiTopK<32>::Params ep{kWarmRows, n_query, thr, cand_s, cand_i, cand_n};
+                EpiTopK<32>::Params ep{kWarmRows, n_query, thr, cand_s, cand_i, cand_n, prog};
                 OFX_TRY((launch_search_cl<32, 4>(q_bf16, n_query, pk, kWarmRows, wp, ep, dim, st)));
             }
         }
         if (W.kcap == 32) {
-            EpiTopK<32>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n};
+            EpiTopK<32>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
             OFX_TRY((launch_search_cl<32, 4>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         } else {
-            EpiTopK<64>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n};
+            EpiTopK<64>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
             OFX_TRY((launch_search_cl<64, 3>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         }
     }

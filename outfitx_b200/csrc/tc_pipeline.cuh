@@ -58,6 +58,7 @@ constexpr int tc_smem_bytes() {
 //   __device__ bool next();          advance to the next tile of this CTA
 //   int m0, n0;                      tile origin (rows of A, rows of B)
 //   static constexpr bool kPrefetch; int pf_n0;   optional: B tile to prefetch into L2 (-1 = none)
+//   static constexpr bool kThrottle; void throttle();   optional: producer-side pacing hook, called once per tile
 // Epi concept:
 //   struct Params; static constexpr int kSmemBytes;
 //   static constexpr int kWarps;   4 or 8 epilogue warps
@@ -138,6 +139,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             int stage = 0;
             uint32_t phase = 0;
             while (sched.next()) {
+                if constexpr (Sched::kThrottle) sched.throttle();
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
                     if constexpr (Sched::kPrefetch) {
                         // designated CTAs pull a LATER B tile of the sweep into L2 (this CTA's rows of it)
