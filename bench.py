@@ -37,6 +37,8 @@ from outfitx_b200 import synth  # noqa: E402
 
 D_MODEL, D_EMBED, DPM, F_FFN, N_LAYERS = 512, 1024, 512, 2024, 6
 N_CAND, TOPK = 4, 10
+CIR_TRAFFIC_BYTES = 32338742069    # same for the main sweep of the search at 8192 queries x 10 M rows on one GPU
+                                   # (profiles/r1_ncu_search_paced.txt; algorithmic: the packed gallery once = 21.76 GB)
 FFN_TRAFFIC_BYTES = 380563456      # dram__bytes_read.sum + dram__bytes_write.sum of one ffn_block_kernel
                                    # launch (LN-emitting form) at 82158 rows (profiles/r1_ncu_ffn_block_ln.txt)
 
@@ -440,7 +442,9 @@ def main():
                                    "one NCCL all-gather + merge", "rows_per_gpu": gal.n_rows,
                        "l2": "gallery shard (bf16) larger than L2"},
             "roofline": {"bound": "tensor", "achieved": cir_tf, "peak": pk["sustained"], "unit": "TFLOP/s",
-                         "frac": cir_tf / pk["sustained"], "traffic": None,
+                         "frac": cir_tf / pk["sustained"],
+                         "traffic": CIR_TRAFFIC_BYTES if (world == 1 and args.cir_rows == 10_000_000 and args.cir_queries == 8192) else None,
+                         "algorithmic_bytes_per_launch": gal.n_rows * (1024 + 64) * 2,
                          "kernel": "tc_kernel<256,4,SchedSearch,EpiTopK<32>> (+ merge_rerank), per GPU",
                          "flops_per_launch": cir_flops, "peak_kind": f"sustained bf16, {pk['source']}"},
             "e2e": {"value": args.cir_queries * k_steps / (cir_e2e_ms * 1e-3), "unit": "queries/s",
