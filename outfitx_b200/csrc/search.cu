@@ -580,7 +580,7 @@ static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     return w;
 }
 
-template <int KCAP, int STAGES, int CL>
+template <int KCAP, int STAGES, int CL, bool PAIR = false>
 static int launch_search(const void* q_bf16, int n_query, const void* gallery, long long n_rows,
                          const SearchPlan& pl, const typename EpiTopK<KCAP>::Params& ep, int dim,
                          cudaStream_t stream) {
@@ -589,8 +589,9 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     const int kdim = dim + kAugCols;   // contraction length including the bias k-block
     OFX_TRY(make_tmap_bf16(&tm_q, q_bf16, static_cast<uint64_t>(n_query), kdim, kdim, kBM));
     OFX_TRY(make_tmap_bf16(&tm_g, gallery, static_cast<uint64_t>(n_rows), kdim, kdim, kSearchBN / CL));
-    auto kern = tc_kernel<kSearchBN, STAGES, CL, SchedSearch, Epi, false>;   // CL = 2: multicast cluster
-    constexpr int smem = tc_smem_bytes<kSearchBN, STAGES, Epi, false>();
+    auto kern = tc_kernel<kSearchBN, STAGES, CL, SchedSearch, Epi, PAIR>;   // CL = 2: multicast cluster or CTA pair
+    constexpr int smem = tc_smem_bytes<kSearchBN, STAGES, Epi, PAIR>();
+    static_assert(smem <= 232448, "search kernel shared memory");
     static bool configured = false;
     if (!configured) {
         OFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -643,6 +644,14 @@ template <int KCAP, int STAGES>
 static int launch_search_cl(const void* q_bf16, int n_query, const void* gallery, long long n_rows,
                             const SearchPlan& pl, const typename EpiTopK<KCAP>::Params& ep, int dim,
                             cudaStream_t stream) {
+    // CTA pairs (cta_group::2, M = 256: each CTA parks only half of the gallery tile, 32 KB stages, 6-deep ring)
+    // are the default since the pacing window removed the HBM traffic: 133.4 vs 137.6 ms at 10 M rows, 20.4 vs
+    // 21.1 ms at 1.25 M.  (Before it the multicast cluster was ahead, 1004 vs 940 TFLOP/s.)  OFX_SEARCH_PAIR=0
+    // selects the multicast cluster.  What is left is L2 -> SM throughput: 1.39 TB per sweep = ~11 TB/s.
+    static int pair = -1;
+    if (pair < 0) { const char* e = getenv("OFX_SEARCH_PAIR"); pair = (e && e[0] == '0') ? 0 : 1; }
+    constexpr int kPairStages = KCAP == 32 ? 6 : 5;
+    if (pl.cl == 2 && pair) return launch_search<KCAP, kPairStages, 2, true>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
     if (pl.cl == 2) return launch_search<KCAP, STAGES, 2>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
     return launch_search<KCAP, STAGES, 1>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
 }

@@ -15,7 +15,8 @@
 //
 // CL == 2, PAIR = false: a multicast cluster -- two CTAs with different A tiles and the SAME B tile;
 // each fetches half of the B rows and TMA-multicasts them into both, every CTA issues its own
-// M = 128 MMAs.  (Best for the search kernel: measured 1004 vs 940 TFLOP/s at 10 M rows.)
+// M = 128 MMAs.  (Was best for the search kernel while it was HBM / power bound: 1004 vs 940 TFLOP/s at
+// 10 M rows; with the pacing window of SchedSearch the pair mode below is 3 % ahead and is its default.)
 // CL == 2, PAIR = true: a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  The two CTAs own consecutive M
 // tiles (256 rows together) and the same B tile (n0); the even CTA issues M = 256 MMAs, each CTA
 // supplies its own 128 rows of A and HALF of the B tile from its own shared memory and receives
