@@ -77,8 +77,10 @@ struct Params {
     __nv_bfloat16* h_next;  // optional (rows, 512) bf16: LayerNorm 1 of the NEXT layer applied to the new x
     const float* lnn_w;     // its affine terms
     const float* lnn_b;
-    int debug;              // OFX_FFN_DEBUG: 1 = skip mish (timing experiments only)
-    long long* prof;        // debug bit 3: per-pair cycle counters of the MMA warp (8 per pair)
+    int debug;              // OFX_FFN_DEBUG bit mask, timing experiments only (results are WRONG with 1 / 256 / 512):
+                            // 1 skip mish, 8 dump cycle counters, 256 skip the residual loads, 512 skip the x stores
+    long long* prof;        // debug bit 3: per-pair cycle counters (16 per pair: MMA-warp waits; with
+                            // -DOFX_FFN_EPROF also the phases of epilogue warp 0)
 };
 
 __device__ __forceinline__ float mish_fast(float x) {
