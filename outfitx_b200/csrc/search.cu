@@ -324,6 +324,77 @@ struct EpiTopK {
 };
 
 // ---------------------------------------------------------------------------------------
+// Threshold seeding epilogue.  For every query the maxima of NB disjoint blocks of 128 gallery rows are
+// NB scores of NB distinct rows, so the m-th largest of them is a lower bound of the m-th best score of
+// the whole gallery -- a valid starting threshold for the top-m lists of the main sweep.  Unlike running
+// the real top-k epilogue over a sample (the previous warm-up: 1.15 ms at 8192 queries, dominated by
+// divergent list insertions while the lists are cold) this is one running maximum per thread and a
+// warp-uniform selection at the end: ~60 us for 64 blocks, and with NB = 2 m the bound (the median of
+// maxima of 128 samples = the 0.54 % quantile) is tighter than the exact m-th best of 4096 rows (0.78 %).
+// ---------------------------------------------------------------------------------------
+template <int NBMAX>
+struct EpiBlockMax {
+    struct Params {
+        long long n_rows;          // rows swept (multiple of kSearchBN, all real)
+        int n_query;
+        uint32_t* thr_enc;
+        int m;                     // which order statistic of the block maxima (= list capacity of the main sweep)
+        int* progress;             // scheduler pacing state (SchedSearch::throttle)
+    };
+    static constexpr int kMaxBlocks = NBMAX;
+    static constexpr int kSmemBytes = kMaxBlocks * 128 * 4;
+    static constexpr int kWarps = 4;
+
+    float* ls;
+    int nb;
+
+    __device__ void begin(const Params&, const SchedSearch&, int quarter, int lane, uint8_t* smem) {
+        ls = reinterpret_cast<float*>(smem) + quarter * 32 + lane;
+        nb = 0;
+    }
+    __device__ void end(const Params&, int) {}
+    __device__ void pre_tile(const Params&, const SchedSearch&, int, int, uint8_t*) {}
+
+    __device__ void tile(const Params& p, const SchedSearch& s, uint32_t t_acc, int quarter, int lane, uint8_t*) {
+        const int row = s.m0 + quarter * 32 + lane;
+        if (s.first) nb = 0;
+#pragma unroll 1
+        for (int b = 0; b < kSearchBN / 128; ++b) {
+            float bm = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(t_acc + b * 128 + c, raw);
+                tmem_ld_wait();
+                float m4[4] = {__uint_as_float(raw[0]), __uint_as_float(raw[1]), __uint_as_float(raw[2]), __uint_as_float(raw[3])};
+#pragma unroll
+                for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[i]));
+                bm = fmaxf(bm, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            }
+            if (nb < kMaxBlocks) ls[nb * 128] = bm;
+            ++nb;
+        }
+        if (s.last) {
+            const int n = min(nb, kMaxBlocks);
+            if (n >= p.m && row < p.n_query) {
+                float kth = -INFINITY;
+                for (int r = 0; r < p.m; ++r) {          // m-th largest by repeated extraction (warp-uniform trip counts)
+                    float mx = -INFINITY;
+                    int mp = 0;
+                    for (int j = 0; j < n; ++j) {
+                        const float v = ls[j * 128];
+                        if (v > mx) { mx = v; mp = j; }
+                    }
+                    kth = mx;
+                    ls[mp * 128] = -INFINITY;
+                }
+                if (kth > -INFINITY) atomicMax(p.thr_enc + row, enc_score(kth));
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // fp32 -> bf16 rows (queries), and gallery packing (bf16 rows + 0.5|g|^2 from the fp32 data)
 // ---------------------------------------------------------------------------------------
 // queries (nq, dim) fp32 -> (nq, dim + kAugCols) bf16 with the bias selector columns
@@ -580,11 +651,10 @@ static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     return w;
 }
 
-template <int KCAP, int STAGES, int CL, bool PAIR = false>
+template <class Epi, int STAGES, int CL, bool PAIR = false>
 static int launch_search(const void* q_bf16, int n_query, const void* gallery, long long n_rows,
-                         const SearchPlan& pl, const typename EpiTopK<KCAP>::Params& ep, int dim,
+                         const SearchPlan& pl, const typename Epi::Params& ep, int dim,
                          cudaStream_t stream) {
-    using Epi = EpiTopK<KCAP>;
     CUtensorMap tm_q, tm_g;
     const int kdim = dim + kAugCols;   // contraction length including the bias k-block
     OFX_TRY(make_tmap_bf16(&tm_q, q_bf16, static_cast<uint64_t>(n_query), kdim, kdim, kBM));
@@ -640,9 +710,9 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     return OFX_OK;
 }
 
-template <int KCAP, int STAGES>
+template <class Epi, int STAGES, int kPairStages>
 static int launch_search_cl(const void* q_bf16, int n_query, const void* gallery, long long n_rows,
-                            const SearchPlan& pl, const typename EpiTopK<KCAP>::Params& ep, int dim,
+                            const SearchPlan& pl, const typename Epi::Params& ep, int dim,
                             cudaStream_t stream) {
     // CTA pairs (cta_group::2, M = 256: each CTA parks only half of the gallery tile, 32 KB stages, 6-deep ring)
     // are the default since the pacing window removed the HBM traffic: 133.4 vs 137.6 ms at 10 M rows, 20.4 vs
@@ -650,10 +720,9 @@ static int launch_search_cl(const void* q_bf16, int n_query, const void* gallery
     // selects the multicast cluster.  What is left is L2 -> SM throughput: 1.39 TB per sweep = ~11 TB/s.
     static int pair = -1;
     if (pair < 0) { const char* e = getenv("OFX_SEARCH_PAIR"); pair = (e && e[0] == '0') ? 0 : 1; }
-    constexpr int kPairStages = KCAP == 32 ? 6 : 5;
-    if (pl.cl == 2 && pair) return launch_search<KCAP, kPairStages, 2, true>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
-    if (pl.cl == 2) return launch_search<KCAP, STAGES, 2>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
-    return launch_search<KCAP, STAGES, 1>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
+    if (pl.cl == 2 && pair) return launch_search<Epi, kPairStages, 2, true>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
+    if (pl.cl == 2) return launch_search<Epi, STAGES, 2>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
+    return launch_search<Epi, STAGES, 1>(q_bf16, n_query, gallery, n_rows, pl, ep, dim, stream);
 }
 
 }  // namespace ofx
@@ -725,30 +794,51 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
             queries, n_query, dim, metric == OFX_METRIC_L2 ? 1.f : 0.f, q_bf16);
         OFX_LAUNCH_CHECK();
         OFX_CUDA(cudaMemsetAsync(thr, 0, static_cast<size_t>(W.plan.n_qgroups) * W.plan.cl * 128 * 4, st));
-        // Threshold warm-up: a sweep over the first few thousand rows leaves each query's kcap-th
-        // best of that sample in thr_enc (a valid lower bound of the final one: the sample is part
-        // of the gallery).  The main sweep's first round of units then starts at the ~1 % quantile
-        // instead of cold, which removes most of the divergent list insertions that dominate on
-        // small shards (1 M rows: 19.5 -> see profiles); its candidate lists are overwritten.
-        static long long kWarmRows = -1;     // OFX_WARM_ROWS (multiple of 256; 0 = no warm-up), default 4096
+        // Threshold seeding (EpiBlockMax): the kcap-th largest of 2 kcap block maxima over the first rows is a
+        // valid lower bound of every query's final kcap-th best, so the main sweep starts near the 0.5 %
+        // quantile instead of cold and most of the divergent list insertions never happen.  OFX_WARM_ROWS sets
+        // the rows swept (multiple of 256, default 64 blocks x 128 = 8192; 0 = off); OFX_WARM_LEGACY=1 runs the
+        // previous warm-up (the real top-k epilogue over 4096 rows, 1.15 ms) for A/B timing.
+        static long long kWarmRows = -1;
+        static int warm_legacy = -1;
         if (kWarmRows < 0) {
             const char* e = getenv("OFX_WARM_ROWS");
-            kWarmRows = e ? atoll(e) : 4096;
-            if (kWarmRows % 256) kWarmRows = 4096;
+            const char* l = getenv("OFX_WARM_LEGACY");
+            warm_legacy = (l && l[0] == '1') ? 1 : 0;
+            kWarmRows = e ? atoll(e) : (warm_legacy ? 4096 : 8192);
+            if (kWarmRows % 256) kWarmRows = warm_legacy ? 4096 : 8192;
         }
-        if (W.kcap == 32 && kWarmRows > 0 && n_rows >= 16 * kWarmRows) {
-            SearchPlan wp = make_plan(kWarmRows, n_query, sm_count());
-            if (wp.cl == W.plan.cl && wp.n_units <= W.plan.n_units) {
-                EpiTopK<32>::Params ep{kWarmRows, n_query, thr, cand_s, cand_i, cand_n, prog};
-                OFX_TRY((launch_search_cl<32, 4>(q_bf16, n_query, pk, kWarmRows, wp, ep, dim, st)));
+        const long long warm_rows = W.kcap == 32 ? kWarmRows : 2 * kWarmRows;    // 2 kcap blocks of 128 rows by default
+        if (kWarmRows > 0 && n_rows >= 16 * warm_rows) {
+            if (warm_legacy) {
+                SearchPlan wp = make_plan(kWarmRows, n_query, sm_count());
+                if (W.kcap == 32 && wp.cl == W.plan.cl && wp.n_units <= W.plan.n_units) {
+                    EpiTopK<32>::Params ep{kWarmRows, n_query, thr, cand_s, cand_i, cand_n, prog};
+                    OFX_TRY((launch_search_cl<EpiTopK<32>, 4, 6>(q_bf16, n_query, pk, kWarmRows, wp, ep, dim, st)));
+                }
+            } else if (warm_rows / 128 >= W.kcap) {
+                SearchPlan wp = W.plan;             // same query blocks / cluster shape, ONE segment over the sample
+                wp.n_tiles = static_cast<int>(warm_rows / kSearchBN);
+                wp.n_seg = 1;
+                wp.seg_tiles = wp.n_tiles;
+                wp.n_units = wp.n_qgroups;
+                const int n_cl = sm_count() / wp.cl;
+                wp.grid = (wp.n_units < n_cl ? wp.n_units : n_cl) * wp.cl;
+                if (W.kcap == 32) {
+                    EpiBlockMax<64>::Params ep{warm_rows, n_query, thr, 32, prog};
+                    OFX_TRY((launch_search_cl<EpiBlockMax<64>, 4, 6>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
+                } else {
+                    EpiBlockMax<128>::Params ep{warm_rows, n_query, thr, 64, prog};
+                    OFX_TRY((launch_search_cl<EpiBlockMax<128>, 3, 5>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
+                }
             }
         }
         if (W.kcap == 32) {
             EpiTopK<32>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
-            OFX_TRY((launch_search_cl<32, 4>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
+            OFX_TRY((launch_search_cl<EpiTopK<32>, 4, 6>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         } else {
             EpiTopK<64>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
-            OFX_TRY((launch_search_cl<64, 3>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
+            OFX_TRY((launch_search_cl<EpiTopK<64>, 3, 5>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         }
     }
     MergeArgs ma{};

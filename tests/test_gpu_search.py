@@ -44,7 +44,9 @@ def test_reference_pool_golden(golden_dir):
 
 @pytest.mark.parametrize("n,nq,k,metric", [
     (20000, 300, 10, "l2"), (20000, 300, 10, "dot"), (5000, 7, 1, "l2"), (100, 130, 16, "dot"),
-    (257, 5, 10, "l2"), (70001, 129, 32, "l2")])
+    (257, 5, 10, "l2"), (70001, 129, 32, "l2"),
+    # large enough for the block-maxima threshold seeding (>= 16 x 8192 rows at k <= 16, 16 x 16384 above)
+    (150_001, 64, 10, "l2"), (270_000, 16, 32, "dot")])
 def test_exact_indices_with_duplicates(n, nq, k, metric):
     gal = synth.make_items(n, 512, seed=n, dup=min(1000, n // 4))
     if metric == "l2":  # break the |g|^2 == 2 degeneracy so that the bias term matters
