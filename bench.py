@@ -445,7 +445,7 @@ def main():
                          "frac": cir_tf / pk["sustained"],
                          "traffic": CIR_TRAFFIC_BYTES if (world == 1 and args.cir_rows == 10_000_000 and args.cir_queries == 8192) else None,
                          "algorithmic_bytes_per_launch": gal.n_rows * (1024 + 64) * 2,
-                         "kernel": "tc_kernel<256,4,SchedSearch,EpiTopK<32>> (+ merge_rerank), per GPU",
+                         "kernel": "tc_kernel<256,6,2,SchedSearch,EpiTopK<32>,pair> (+ EpiBlockMax seeding launch, merge_rerank), per GPU",
                          "flops_per_launch": cir_flops, "peak_kind": f"sustained bf16, {pk['source']}"},
             "e2e": {"value": args.cir_queries * k_steps / (cir_e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": q_host.numel() * 4, "d2h_bytes_per_step": idx_host.numel() * 8},
