@@ -75,7 +75,9 @@ struct SchedSearch {
         if ((it & (p.check - 1)) != 0 || it == 0 || last) return;
         const int seg = unit / p.n_qgroups, round = unit / step;
         const int base = seg * p.n_qgroups;
-        for (;;) {
+        // bounded: pacing is an optimisation, never a correctness condition -- after ~20 ms of waiting the unit
+        // simply goes on (a wedged peer must not be able to hang the sweep)
+        for (int spins = 0; spins < (1 << 14); ++spins) {
             int mn = 0x7fffffff;
             if ((p.n_qgroups & 3) == 0) {      // 16-byte loads, all in flight before the first use
                 int4 v[16];
