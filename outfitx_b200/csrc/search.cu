@@ -462,10 +462,12 @@ struct MergeArgs {
     double* out_score;          // (nq, k)
     long long* out_idx;         // (nq, k)
     const uint32_t* thr_enc;    // per-query encoded threshold left by pass 1 (<= the global kcap-th best)
+    unsigned long long* prof;   // OFX_MERGE_PROF=1: [0..3] summed cycles of gather / sort / re-score / rank, [4] CTAs that sorted all keys
 };
 
 constexpr int kMergeThreads = 256;
-constexpr int kMergeSmall = 128;   // candidates that survive the threshold pre-filter
+constexpr int kMergeSmall = 512;   // capacity of the selected-key buffer (power of two)
+constexpr int kMergeSelect = 128;  // with more candidates than this, select before sorting
 constexpr int kMaxRerank = 64;
 
 __global__ void __launch_bounds__(kMergeThreads)
@@ -476,16 +478,16 @@ merge_rerank_kernel(const MergeArgs a) {
     __shared__ int n_valid;
     const int q = blockIdx.x, tid = threadIdx.x;
     const int qb = q / kBM, r = q % kBM;
-    __shared__ int n_small;
-    if (tid == 0) { n_valid = 0; n_small = 0; }
+    __shared__ int n_small, sel_bin;
+    __shared__ unsigned int es_lo, es_hi;
+    __shared__ int hist[256];
+    if (tid == 0) { n_valid = 0; n_small = 0; es_lo = 0xFFFFFFFFu; es_hi = 0u; sel_bin = -1; }
+    hist[tid] = 0;     // kMergeThreads == 256
     __syncthreads();
-    // Every unit's kcap-th best score is a lower bound of the GLOBAL kcap-th best, and pass 1 left
-    // the maximum of those bounds in thr_enc: anything below it cannot be among the kcap best
-    // overall.  Usually only a few dozen of the n_seg * kcap candidates survive, and sorting 128
-    // keys instead of up to 2048 takes the merge from ~2.5 ms to a fraction of that.
-    const uint32_t thr = a.thr_enc ? a.thr_enc[q] : 0u;
+    const long long tstart = a.prof ? clock64() : 0;
     unsigned long long* small = keys + a.n_pad;
     int mine = 0;
+    uint32_t my_lo = 0xFFFFFFFFu, my_hi = 0u;
     for (int e = tid; e < a.n_pad; e += kMergeThreads) {
         const int seg = e / a.kcap, j = e - seg * a.kcap;
         unsigned long long key = 0ull;
@@ -497,23 +499,75 @@ merge_rerank_kernel(const MergeArgs a) {
                 const uint32_t es = enc_score(s);
                 key = (static_cast<unsigned long long>(es) << 32) | (0xFFFFFFFFu - idx);
                 ++mine;
-                if (es >= thr) {
+                my_lo = min(my_lo, es);
+                my_hi = max(my_hi, es);
+            }
+        }
+        keys[e] = key;
+    }
+    if (mine) { atomicAdd(&n_valid, mine); atomicMin(&es_lo, my_lo); atomicMax(&es_hi, my_hi); }
+    __syncthreads();
+    // Selection instead of a full sort.  The n_seg lists of a query hold up to n_seg * kcap candidates, all of
+    // them near the top of the score distribution (each unit keeps ITS kcap best), so a score threshold left
+    // by pass 1 filters almost nothing once the gallery is cut into many segments (measured: every query fell
+    // back to the 2048-key bitonic sort, 55 % of this kernel).  A 256-bin histogram of the encoded scores over
+    // [min, max] finds the bin that holds the kcap-th best; only the keys in that bin or above (kcap plus the
+    // bin's population, typically < 128) are sorted.
+    if (n_valid > kMergeSelect) {
+        const unsigned long long span = static_cast<unsigned long long>(es_hi - es_lo) + 1ull;
+        for (int e = tid; e < a.n_pad; e += kMergeThreads) {
+            const unsigned long long key = keys[e];
+            if (key) atomicAdd(&hist[static_cast<int>(((static_cast<unsigned long long>(static_cast<uint32_t>(key >> 32) - es_lo)) << 8) / span)], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {      // suffix sums from the top bin down, 8 bins per lane
+            int loc = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) loc += hist[255 - (tid * 8 + i)];
+            int inc = loc;   // inclusive scan over lanes (lane 0 = top 8 bins)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += v;
+            }
+            const int before = inc - loc;
+            if (before < a.kcap && inc >= a.kcap) {      // exactly one lane: the kcap-th best lies in its 8 bins
+                int c = before;
+                for (int i = 0; i < 8; ++i) {
+                    c += hist[255 - (tid * 8 + i)];
+                    if (c >= a.kcap) { sel_bin = 255 - (tid * 8 + i); break; }
+                }
+            }
+        }
+        __syncthreads();
+        if (sel_bin >= 0) {
+            for (int e = tid; e < a.n_pad; e += kMergeThreads) {
+                const unsigned long long key = keys[e];
+                if (key && static_cast<int>(((static_cast<unsigned long long>(static_cast<uint32_t>(key >> 32) - es_lo)) << 8) / span) >= sel_bin) {
                     const int pos = atomicAdd(&n_small, 1);
                     if (pos < kMergeSmall) small[pos] = key;
                 }
             }
         }
-        keys[e] = key;
+        __syncthreads();
+    } else if (a.n_pad > kMergeSelect) {     // few candidates in many (mostly empty) lists: compact them
+        for (int e = tid; e < a.n_pad; e += kMergeThreads) {
+            const unsigned long long key = keys[e];
+            if (key) small[atomicAdd(&n_small, 1)] = key;
+        }
+        if (tid == 0) sel_bin = 0;
+        __syncthreads();
     }
-    if (mine) atomicAdd(&n_valid, mine);
-    __syncthreads();
-    const bool use_small = n_small <= kMergeSmall && (n_small >= a.kcap || n_small == n_valid);
+    const bool use_small = sel_bin >= 0 && n_small <= kMergeSmall && (n_small >= a.kcap || n_small == n_valid);
+    long long tp0 = 0, tp1 = 0, tp2 = 0;
+    if (a.prof && tid == 0) { tp1 = clock64(); atomicAdd(a.prof + 0, static_cast<unsigned long long>(tp1 - tstart)); if (!use_small) atomicAdd(a.prof + 4, 1ull); }
     int sort_n = a.n_pad;
     unsigned long long* sk = keys;
     if (use_small) {
-        for (int e = n_small + tid; e < kMergeSmall; e += kMergeThreads) small[e] = 0ull;
+        sort_n = 32;
+        while (sort_n < n_small) sort_n <<= 1;
+        for (int e = n_small + tid; e < sort_n; e += kMergeThreads) small[e] = 0ull;
         sk = small;
-        sort_n = kMergeSmall;
         __syncthreads();
     }
     // bitonic sort, descending
@@ -529,10 +583,21 @@ merge_rerank_kernel(const MergeArgs a) {
             __syncthreads();
         }
     }
+    if (a.prof && tid == 0) { tp2 = clock64(); atomicAdd(a.prof + 1, static_cast<unsigned long long>(tp2 - tp1)); }
     if (use_small && tid == 0) n_valid = n_small;
     __syncthreads();
     const int n_r = min(min(n_valid, a.kcap), kMaxRerank);
     const int warp = tid >> 5, lane = tid & 31;
+    // the gallery rows of the candidates are cold 4 KB reads scattered over HBM: every warp asks for all of its
+    // rows at once (one 128-byte line per lane and row) before it starts on the first
+    if (a.gallery_f32) {
+        for (int c = warp; c < n_r; c += kMergeThreads / 32) {
+            const long long idx = 0xFFFFFFFFu - static_cast<uint32_t>(sk[c] & 0xFFFFFFFFull);
+            const float* g = a.gallery_f32 + idx * a.dim;
+            for (int d = lane * 32; d < a.dim; d += 1024)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(g + d));
+        }
+    }
     for (int c = warp; c < n_r; c += kMergeThreads / 32) {
         const unsigned long long key = sk[c];
         const long long idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
@@ -541,10 +606,22 @@ merge_rerank_kernel(const MergeArgs a) {
             const float* g = a.gallery_f32 + idx * a.dim;
             const float* qv = a.queries + static_cast<long long>(q) * a.dim;
             double acc = 0.0, nn = 0.0;
-            for (int d = lane; d < a.dim; d += 32) {
-                const double gv = static_cast<double>(g[d]);
-                acc = fma(static_cast<double>(qv[d]), gv, acc);
-                nn = fma(gv, gv, nn);
+            // eight gallery elements per lane in flight (the row is a cold 4 KB read from HBM; as a rolled loop
+            // its 32 iterations were 32 exposed round trips); same element order per lane as before
+            for (int d0 = lane; d0 < a.dim; d0 += 256) {
+                float gv[8], qq[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int d = d0 + 32 * u;
+                    gv[u] = d < a.dim ? __ldcs(g + d) : 0.f;
+                    qq[u] = d < a.dim ? __ldg(qv + d) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double gd = static_cast<double>(gv[u]);
+                    acc = fma(static_cast<double>(qq[u]), gd, acc);
+                    nn = fma(gd, gd, nn);
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -558,6 +635,7 @@ merge_rerank_kernel(const MergeArgs a) {
         if (lane == 0) { r_score[c] = score; r_idx[c] = idx; }
     }
     __syncthreads();
+    if (a.prof && tid == 0) { tp0 = clock64(); atomicAdd(a.prof + 2, static_cast<unsigned long long>(tp0 - tp2)); }
     if (tid < a.k) {
         const long long o = static_cast<long long>(q) * a.k + tid;
         if (tid >= n_r) { a.out_score[o] = -INFINITY; a.out_idx[o] = -1; }
@@ -852,6 +930,14 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
     ma.queries = queries; ma.gallery_f32 = gallery_f32; ma.dim = dim; ma.metric = metric; ma.k = k;
     ma.id_offset = id_offset; ma.out_score = out_score; ma.out_idx = reinterpret_cast<long long*>(out_idx);
     ma.thr_enc = n_rows > 0 ? thr : nullptr;
+    static int merge_prof = -1;
+    static unsigned long long* merge_prof_dev = nullptr;
+    if (merge_prof < 0) { const char* e = getenv("OFX_MERGE_PROF"); merge_prof = (e && e[0] == '1') ? 1 : 0; }
+    if (merge_prof) {
+        if (!merge_prof_dev) OFX_CUDA(cudaMalloc(&merge_prof_dev, 64));
+        OFX_CUDA(cudaMemsetAsync(merge_prof_dev, 0, 64, st));
+    }
+    ma.prof = merge_prof ? merge_prof_dev : nullptr;
     const size_t smem = static_cast<size_t>(n_pad + kMergeSmall) * 8;
     static bool configured = false;
     if (!configured) {
@@ -860,6 +946,13 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
     }
     merge_rerank_kernel<<<n_query, kMergeThreads, smem, st>>>(ma);
     OFX_LAUNCH_CHECK();
+    if (merge_prof) {     // debug only: synchronous dump
+        unsigned long long h[8];
+        OFX_CUDA(cudaStreamSynchronize(st));
+        OFX_CUDA(cudaMemcpy(h, merge_prof_dev, 64, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "merge prof (avg cycles per query CTA): gather %llu  sort %llu  re-score %llu ; full sorts %llu of %d ; n_pad %d n_seg %d\n",
+                h[0] / n_query, h[1] / n_query, h[2] / n_query, h[4], n_query, n_pad, W.plan.n_seg);
+    }
     return OFX_OK;
 }
 
