@@ -466,12 +466,15 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
             }
             EPROF_END(e_res);
             tc_fence_before();
+            // x_done: the LayerNorm warps may re-read the new rows.  Every lane fences its global stores at CTA
+            // scope before the warp converges; lane 0's mbarrier.arrive (release) then publishes them and the
+            // LayerNorm warps acquire through mbarrier.try_wait.  (Measured: the fence costs nothing here.)
+            if (p.h_next) __threadfence_block();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(a2empty);
-            // x_done: the LayerNorm warps may re-read the new rows.  The global stores above are ordered before
-            // the arrival by __syncwarp (memory ordering among the warp's lanes) + the release semantics of
-            // mbarrier.arrive; the LayerNorm warps acquire through mbarrier.try_wait.
-            if (p.h_next && lane == 0) mbar_arrive(x_done);
+            if (lane == 0) {
+                mbar_arrive_cluster(a2empty);
+                if (p.h_next) mbar_arrive(x_done);
+            }
         }
 #ifdef OFX_FFN_EPROF
         if (eprof && lane == 0) {
