@@ -546,9 +546,14 @@ constexpr int kAttnMaxS = 17;
 // (still >= 512 contiguous bytes per row), so a CTA needs 1 / NSPLIT of the shared memory and twice
 // as many CTAs are resident per SM -- the kernel is latency-bound (gather -> compute -> store with no
 // overlap inside a CTA), so residency is what hides the gather.
-template <int HD, bool BIG, int NSPLIT>
+// SMALL: S <= 8 tokens (40 % of the outfits at n ~ U{2..16}): only query rows 0..7 (h = 0) and the first
+// 8-key n-tile exist, so the second score MMA, half of the softmax and half of the output stores are skipped.
+template <int HD, bool BIG, int NSPLIT, bool SMALL = false>
 __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* sm) {
+    static_assert(!(BIG && SMALL), "one or the other");
     constexpr int MT = BIG ? 2 : 1, KT = BIG ? 2 : 1;
+    constexpr int NH = SMALL ? 1 : 2;            // row halves (g, g + 8) in use
+    constexpr int NNT = SMALL ? 1 : 2 * KT;      // 8-key n-tiles in use
     constexpr int DM = 16 * HD / NSPLIT;     // columns this CTA serves
     constexpr int HPW = 4 / NSPLIT;          // heads per warp
     constexpr int CPR = DM / 8;              // 16-byte chunks per row
@@ -636,7 +641,7 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
                     for (int mt = 0; mt < MT; ++mt) {
                         if (mt < n_mt) {
                             mma_bf16_16816(sc[mt][2 * kt], qa[mt], kb[0], kb[1]);
-                            mma_bf16_16816(sc[mt][2 * kt + 1], qa[mt], kb[2], kb[3]);
+                            if constexpr (!SMALL) mma_bf16_16816(sc[mt][2 * kt + 1], qa[mt], kb[2], kb[3]);
                         }
                     }
                 }
@@ -649,10 +654,10 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
         for (int mt = 0; mt < MT; ++mt) {
             if (mt < n_mt) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {       // h = 0: row g, h = 1: row g + 8
+                for (int h = 0; h < NH; ++h) {      // h = 0: row g, h = 1: row g + 8
                     float mx = -INFINITY;
 #pragma unroll
-                    for (int nt = 0; nt < 2 * KT; ++nt)
+                    for (int nt = 0; nt < NNT; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             float v = (kvalid >> (nt * 2 + e)) & 1u ? sc[mt][nt][2 * h + e] * sl2 : -INFINITY;
@@ -663,7 +668,7 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
                     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
                     float sum = 0.f;
 #pragma unroll
-                    for (int nt = 0; nt < 2 * KT; ++nt)
+                    for (int nt = 0; nt < NNT; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const float pz = ex2_fast(sc[mt][nt][2 * h + e] - mx);   // key 0 is always valid: mx finite
@@ -677,9 +682,13 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
 #pragma unroll
                 for (int kt = 0; kt < KT; ++kt) {
                     pa[mt][kt][0] = pack2_bf16(sc[mt][2 * kt][0], sc[mt][2 * kt][1]);
-                    pa[mt][kt][1] = pack2_bf16(sc[mt][2 * kt][2], sc[mt][2 * kt][3]);
-                    pa[mt][kt][2] = pack2_bf16(sc[mt][2 * kt + 1][0], sc[mt][2 * kt + 1][1]);
-                    pa[mt][kt][3] = pack2_bf16(sc[mt][2 * kt + 1][2], sc[mt][2 * kt + 1][3]);
+                    if constexpr (SMALL) {     // rows 8..15 and keys 8..15 do not exist
+                        pa[mt][kt][1] = pa[mt][kt][2] = pa[mt][kt][3] = 0u;
+                    } else {
+                        pa[mt][kt][1] = pack2_bf16(sc[mt][2 * kt][2], sc[mt][2 * kt][3]);
+                        pa[mt][kt][2] = pack2_bf16(sc[mt][2 * kt + 1][0], sc[mt][2 * kt + 1][1]);
+                        pa[mt][kt][3] = pack2_bf16(sc[mt][2 * kt + 1][2], sc[mt][2 * kt + 1][3]);
+                    }
                 }
             }
         }
@@ -714,7 +723,7 @@ __device__ __forceinline__ void attention_mma_body(const AttnArgs& a, uint8_t* s
             for (int mt = 0; mt < MT; ++mt) {
                 if (mt < n_mt) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < NH; ++h) {
                         const int r = mt * 16 + g + 8 * h;
                         if (r < n_q) {
 #pragma unroll
@@ -741,7 +750,9 @@ __global__ void __launch_bounds__(128)
 attention_mma_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) uint8_t attn_sm[];
     const int b = blockIdx.x;
-    if (a.off[b + 1] - a.off[b] < 16) attention_mma_body<HD, false, NSPLIT>(a, attn_sm);   // S = 1 + n <= 16
+    const int n_items = a.off[b + 1] - a.off[b];
+    if (n_items < 8 && a.small_ok) attention_mma_body<HD, false, NSPLIT, true>(a, attn_sm);   // S = 1 + n <= 8
+    else if (n_items < 16) attention_mma_body<HD, false, NSPLIT>(a, attn_sm);         // S <= 16
     else attention_mma_body<HD, true, NSPLIT>(a, attn_sm);
 }
 
@@ -753,7 +764,11 @@ static int launch_attention_mma_split(const AttnArgs& a, cudaStream_t stream) {
         OFX_CUDA(cudaFuncSetAttribute(attention_mma_kernel<HD, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    attention_mma_kernel<HD, NSPLIT><<<dim3(a.batch, NSPLIT), 128, smem, stream>>>(a);
+    static int small_ok = -1;    // OFX_ATTN_SMALL=0: no S <= 8 specialisation (A/B timing)
+    if (small_ok < 0) { const char* e = getenv("OFX_ATTN_SMALL"); small_ok = (e && e[0] == '0') ? 0 : 1; }
+    AttnArgs b = a;
+    b.small_ok = small_ok;
+    attention_mma_kernel<HD, NSPLIT><<<dim3(a.batch, NSPLIT), 128, smem, stream>>>(b);
     OFX_LAUNCH_CHECK();
     return OFX_OK;
 }

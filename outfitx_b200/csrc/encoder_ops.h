@@ -32,6 +32,7 @@ struct AttnArgs {
     const void* k; long long ldk;
     const void* v; long long ldv;
     void* out; long long ldo;
+    int small_ok = 1;      // allow the S <= 8 body of the tensor-core attention kernel
 };
 
 // fused LN2 -> linear1 -> mish -> linear2 -> +residual on the fp32 residual stream (ffn_block.cu)
