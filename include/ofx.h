@@ -148,16 +148,6 @@ typedef struct ofx_forward_args {
     int64_t n_cand_rows;
 } ofx_forward_args;
 
-/* ---- host -> device transfer of a collated batch, valid slots only.  The reference copies the padded
- * (B, max_items, dpm) tensors whole (`v.to(local_rank)`, compatibility_prediction_trainer.py:140-145);
- * here the SMs read the PINNED host tensors host_img / host_txt directly (unified addressing) and copy only
- * the slots whose mask byte is 0 into dev_img / dev_txt (same layout; padded slots are left untouched --
- * ofx_encoder_forward never reads them).  mask is a DEVICE pointer.  Fails with OFX_E_ARG on pageable
- * host memory. */
-OFX_API int ofx_fetch_valid_items(const float* host_img, const float* host_txt, const uint8_t* mask,
-                          int32_t batch, int32_t max_items, int32_t dpm, float* dev_img,
-                          float* dev_txt, void* stream);
-
 OFX_API size_t ofx_encoder_workspace_bytes(const ofx_shape* shape, int32_t batch);
 OFX_API int ofx_encoder_forward(const ofx_shape* shape, const void* packed_weights,
                         const ofx_forward_args* args, void* workspace, size_t workspace_bytes,
@@ -169,18 +159,32 @@ OFX_API int ofx_encoder_forward(const ofx_shape* shape, const void* packed_weigh
  * q.g (OFX_METRIC_DOT); ties are broken by the lowest gallery index. */
 OFX_API size_t ofx_gallery_packed_bytes(int64_t n_rows, int32_t dim);
 /* gallery (n_rows, dim) fp32 -> packed bf16 rows of dim + 64 columns (the extra k-block carries
- * -0.5|g|^2 as bf16 hi + lo, so the L2 bias is part of the contraction) + fp32 0.5|g|^2 */
+ * -0.5|g|^2 as bf16 hi + lo, so the L2 bias is part of the contraction) + fp32 0.5|g|^2 per row + its
+ * maximum over the shard (used by the exactness certificate) */
 OFX_API int ofx_gallery_pack(const float* gallery, int64_t n_rows, int32_t dim, void* packed,
                      void* stream);
 OFX_API size_t ofx_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_query, int32_t k);
-/* Exact top-k of every query over this shard's rows.  Candidates come from a bf16 tcgen05
+/* Exact top-k (k <= 64) of every query over this shard's rows.  Candidates come from a bf16 tcgen05
  * pass with a fused per-row top-k' selection (the score matrix never reaches HBM); they are
  * re-scored in fp64 from the fp32 gallery and ranked by (-score, index).  out_idx carries
- * GLOBAL ids (id_offset + local row); slots beyond n_rows get idx -1 / score -inf. */
+ * GLOBAL ids (id_offset + local row); slots beyond n_rows get idx -1 / score -inf.
+ * out_certified (n_query bytes, may be NULL): 1 = PROVEN equal to the exhaustive fp64 result -- the k-th
+ * best exact score clears every score the bf16 pass may have dropped by a rigorous bound on the bf16
+ * error (|q| max|g| (2^-8 + ...)); candidates inside that band are re-scored as well.  0 = not proven
+ * (gallery rows closer to each other than bf16 resolves, more of them than the lists hold): run
+ * ofx_exact_search on those queries.  Always 0 when gallery_f32 == NULL (bf16 ranking requested). */
 OFX_API int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows, int32_t dim,
                     int64_t id_offset, const float* queries, int32_t n_query, int32_t k,
-                    int32_t metric, double* out_score, int64_t* out_idx, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    int32_t metric, double* out_score, int64_t* out_idx, uint8_t* out_certified,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* Exhaustive fp64 search of the n_sel queries listed in sel (device int32 query indices): the fallback for
+ * uncertified queries.  Rows sel[i] of out_score / out_idx (n_query, k) are overwritten (and out_certified[sel[i]]
+ * set to 1 when given); cost is one pass over the fp32 gallery per 8 selected queries. */
+OFX_API size_t ofx_exact_search_workspace_bytes(int64_t n_rows, int32_t n_sel, int32_t k);
+OFX_API int ofx_exact_search(const float* gallery_f32, int64_t n_rows, int32_t dim, int64_t id_offset,
+                     const float* queries, const int32_t* sel, int32_t n_sel, int32_t k, int32_t metric,
+                     double* out_score, int64_t* out_idx, uint8_t* out_certified, void* workspace,
+                     size_t workspace_bytes, void* stream);
 /* Merge R per-shard lists (R, nq, k) by (-score, idx) into (nq, k): the step after the NCCL
  * all-gather of the gallery-sharded search (no reference counterpart: its inference is
  * single-GPU, complementary_item_retrieval_trainer.py:350-351). */
@@ -234,17 +238,21 @@ OFX_API int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw
  * (torch TransformerEncoderLayer._ff_block as configured at outfit_x.py:32-45).
  * x (rows, d_model) fp32; w1 (d_ffn_padded, d_model) bf16; w2 (d_model, d_ffn_padded) bf16;
  * b1 (d_ffn_padded), b2 / ln_w / ln_b (d_model) fp32.  d_model == 512, d_ffn_padded % 256 == 0. */
+OFX_API size_t ofx_ffn_block_workspace_bytes(int32_t rows, int32_t d_model, int32_t d_ffn_padded);
 OFX_API int ofx_ffn_block_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_padded,
                        const float* ln_w, const float* ln_b, const void* w1, const float* b1,
-                       const void* w2, const float* b2, void* stream);
+                       const void* w2, const float* b2, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* Same block, and in the same kernel h_next (rows, d_model) bf16 <- LayerNorm(x_new; next_ln_w,
  * next_ln_b): norm1 of the FOLLOWING encoder layer (transformer.py:944-947), computed by otherwise idle
- * warps from the rows the block has just written, so the inter-layer LayerNorm kernel disappears. */
+ * warps from the rows the block has just written, so the inter-layer LayerNorm kernel disappears.
+ * workspace (256-byte aligned, ofx_ffn_block_workspace_bytes): the ring through which the cooperating CTA
+ * pairs exchange bf16 hidden chunks, plus their counters; contents are scratch. */
 OFX_API int ofx_ffn_block_ln_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_padded,
                           const float* ln_w, const float* ln_b, const void* w1, const float* b1,
                           const void* w2, const float* b2, void* h_next, const float* next_ln_w,
-                          const float* next_ln_b, void* stream);
+                          const float* next_ln_b, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

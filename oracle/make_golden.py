@@ -26,8 +26,16 @@ from oracle import ref_shim  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
-# (name, fusion, d_model, batch): lengths are drawn by case_inputs below
-CASES = [("concat1024", "concat", 1024, 8), ("mean512", "mean", 512, 8)]
+# (name, fusion, d_model, batch): lengths are drawn by case_inputs below.  slip1536 is the reference's DEFAULT
+# configuration (ItemEncoderConfig.type = 'slip': 768 per modality, d_model 1536, head_dim 96,
+# src/models/configs/item_encoder_config.py:9,24-26).
+CASES = [("concat1024", "concat", 1024, 8), ("mean512", "mean", 512, 8), ("slip1536", "concat", 1536, 8)]
+
+
+def case_dims(method: str, d_model: int):
+    """-> (dim_per_modality, cfg.d_embed = 2 * dim_per_modality, encoder type)."""
+    dpm = d_model // 2 if method == "concat" else d_model
+    return dpm, 2 * dpm, ("slip" if dpm == 768 else "clip")
 
 
 def digest(*arrays) -> str:
@@ -37,10 +45,10 @@ def digest(*arrays) -> str:
     return h.hexdigest()[:16]
 
 
-def case_inputs(method: str, batch: int, seed: int = 100):
+def case_inputs(method: str, batch: int, seed: int = 100, dpm: int = 512):
     """Inputs of a golden case: ragged lengths incl. the edge cases 0, 1 and 16 items, plus
     one outfit whose valid items are NOT left-aligned (the model must not care)."""
-    img, txt = synth.make_modalities(batch, 512, seed)
+    img, txt = synth.make_modalities(batch, dpm, seed)
     lengths = synth.make_lengths(batch, seed + 1)
     lengths[:3] = (0, 1, 16)
     mask = synth.make_mask(lengths)
@@ -49,8 +57,68 @@ def case_inputs(method: str, batch: int, seed: int = 100):
     emb[mask] = 0.0
     d_model = emb.shape[-1]
     text = synth.make_text_prefix(batch, d_model // 2, seed + 2)
-    cand = synth.make_items(batch * 4, 512, seed + 3).reshape(batch, 4, 1024)
+    cand = synth.make_items(batch * 4, dpm, seed + 3).reshape(batch, 4, 2 * dpm)
     return img, txt, emb, mask, text, cand
+
+
+def processor_items(seed: int = 500):
+    """Raw material of the collate fixture: per outfit a list of item embeddings (ragged: 1, 3, 16, 20 -> truncated
+    to 16, 7, 2 items), the target item's embedding and 4 FITB candidates.  1024-d fused items (clip + concat)."""
+    lengths = [1, 3, 16, 20, 7, 2]
+    pool = synth.make_items(sum(lengths) + len(lengths) * 5, 512, seed)
+    outfits, targets, cands, at = [], [], [], 0
+    for n in lengths:
+        outfits.append([pool[at + i] for i in range(n)])
+        at += n
+        targets.append(pool[at])
+        cands.append(np.stack([pool[at + 1 + j] for j in range(4)]))
+        at += 5
+    return outfits, targets, cands
+
+
+def write_processor_golden(out_dir: str = OUT):
+    """The reference's OWN collate (outfit_x_base_processor.py:20-81, CP processor :7-22, CIR processor :95-114,
+    FITB processor :9-40) run on lists of its own pydantic task objects; the tensors it emits and what the
+    reference model answers to them."""
+    ox, cfgs, dts = ref_shim.load_reference()
+    from src.models.processor.outfit_x.outfit_x_compatibility_prediction_task_processor import (
+        OutfitXCompatibilityPredictionTaskProcessor)
+    from src.models.processor.outfit_x.outfit_x_complementary_item_retrieval_processor import (
+        OutfitXComplementaryItemRetrievalTaskProcessor)
+    from src.models.processor.outfit_x.outfit_x_fill_in_the_blank_task_processor import (
+        OutfitXFillInTheBlankTaskProcessor)
+    cfg = cfgs.OutfitXConfig(item_encoder=cfgs.ItemEncoderConfig(type="clip", aggregation_method="concat"))
+    outfits, targets, cands = processor_items()
+    item = lambda e, i: dts.FashionItem(item_id=i, embedding=e, text_embedding=e[512:])   # text = second half
+    # (polyvore_item_dataset.py:75)
+    cp_batch = [(dts.OutfitCompatibilityPredictionTask(outfit=[item(e, i) for i, e in enumerate(o)]), float(b % 2))
+                for b, o in enumerate(outfits)]
+    cir_batch = [(dts.OutfitComplementaryItemRetrievalTask(outfit=[item(e, i) for i, e in enumerate(o)],
+                                                           target_item=item(t, 1000 + b)), None)
+                 for b, (o, t) in enumerate(zip(outfits, targets))]
+    fitb_batch = [(dts.OutfitFillInTheBlankTask(outfit=[item(e, i) for i, e in enumerate(o)], target_item=item(t, 1000 + b)),
+                   torch.from_numpy(c), b % 4)
+                  for b, (o, t, c) in enumerate(zip(outfits, targets, cands))]
+    cp = OutfitXCompatibilityPredictionTaskProcessor(cfg)(cp_batch)
+    cir = OutfitXComplementaryItemRetrievalTaskProcessor("test", cfg)(cir_batch)
+    fitb = OutfitXFillInTheBlankTaskProcessor(cfg)(fitb_batch)
+    sd = synth.make_state_dict(1024, 1024, seed=0)
+    model = ref_shim.build_reference_model("concat", sd)
+    logits = model(**cp["input_dict"])
+    query = model(**cir["input_dict"])
+    q_fitb = model(**fitb["input_dict"])
+    d = torch.cdist(q_fitb.unsqueeze(1), fitb["candidate_item_embedding"], p=2).squeeze(1)   # fitb trainer :52-53
+    np.savez_compressed(
+        os.path.join(out_dir, "processor_clip1024.npz"), seed=500, weight_seed=0,
+        cp_outfit_embedding=cp["input_dict"]["outfit_embedding"].numpy(), cp_outfit_mask=cp["input_dict"]["outfit_mask"].numpy(),
+        cp_task=cp["input_dict"]["task"].__name__, cp_label=cp["label"].numpy(),
+        cir_outfit_embedding=cir["input_dict"]["outfit_embedding"].numpy(), cir_outfit_mask=cir["input_dict"]["outfit_mask"].numpy(),
+        cir_text=cir["input_dict"]["target_item_text_embedding"].numpy(), cir_task=cir["input_dict"]["task"].__name__,
+        cir_pos_item_id=np.asarray(cir["pos_item_id"]),
+        fitb_task=fitb["input_dict"]["task"].__name__, fitb_cand=fitb["candidate_item_embedding"].numpy(),
+        fitb_answer=fitb["answer_index"].numpy(),
+        logits=logits.numpy(), query=query.numpy(), fitb_dists=d.numpy(), fitb_argmin=torch.argmin(d, -1).numpy())
+    print("processor_clip1024.npz: logits", logits.flatten()[:3].tolist(), "mask rows", cp["input_dict"]["outfit_mask"].sum(-1).tolist())
 
 
 def loss_inputs(seed: int = 400):
@@ -112,17 +180,23 @@ def write_loss_golden(out_dir: str = OUT):
     print("losses.npz: focal mean", float(out["focal_g2_a0.5_mean"]), "rank", float(out["rank_m2.0"]), "auc", auc)
 
 
-def main():
+def main(only=None):
+    """only: names of the fixtures to (re)write (model cases by name, 'processor', 'fusion', 'search', 'losses');
+    None = all.  Existing fixtures are byte-stable under regeneration on the same torch build."""
     assert ref_shim.available(), "reference not mounted"
     os.makedirs(OUT, exist_ok=True)
     ox, cfgs, dts = ref_shim.load_reference()
     torch.set_grad_enabled(False)
+    want = lambda n: only is None or n in only
 
     for name, method, d_model, batch in CASES:
-        sd = synth.make_state_dict(d_model, 1024, seed=0)
-        model = ref_shim.build_reference_model(method, sd)
-        assert model.item_encoder.d_embed == d_model
-        img, txt, emb, mask, text, cand = case_inputs(method, batch)
+        if not want(name):
+            continue
+        dpm, d_embed, enc_type = case_dims(method, d_model)
+        sd = synth.make_state_dict(d_model, d_embed, seed=0)
+        model = ref_shim.build_reference_model(method, sd, encoder_type=enc_type)
+        assert model.item_encoder.d_embed == d_model and model.cfg.d_embed == d_embed
+        img, txt, emb, mask, text, cand = case_inputs(method, batch, dpm=dpm)
         t = torch.from_numpy
         logits = model(task=dts.OutfitCompatibilityPredictionTask,
                        outfit_embedding=t(emb), outfit_mask=t(mask))
@@ -143,6 +217,12 @@ def main():
             fitb_dists=dists.numpy(), fitb_argmin=fitb_idx.numpy())
         print(name, "logits", logits.flatten()[:4].tolist())
 
+    if want("processor"):
+        write_processor_golden()
+    if want("losses"):
+        write_loss_golden()
+    if not want("fusion") and not want("search"):
+        return
     # fusion contract: F.normalize per modality then aggregate_embeddings (concat)
     import torch.nn.functional as F
     from src.utils.model_utils import aggregate_embeddings
@@ -162,9 +242,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "search_pool3000.npz"), pool_seed=300, query_seed=301,
                         input_digest=digest(pool, q), indices=tk.indices.numpy(),
                         dists=tk.values.numpy())
-    write_loss_golden()
     print("golden fixtures written to", OUT)
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:] or None)

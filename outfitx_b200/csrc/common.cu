@@ -31,7 +31,7 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
-static int g_sm_count = 0;
+static int g_sm_count[DeviceOnce::kMaxDevices] = {};
 
 int require_sm100() {
     int dev = 0;
@@ -44,15 +44,13 @@ int require_sm100() {
 }
 
 int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_sm_count = n;
-        else
-            g_sm_count = 148;
-    }
-    return g_sm_count;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DeviceOnce::kMaxDevices) return 148;
+    const int cached = __atomic_load_n(&g_sm_count[dev], __ATOMIC_RELAXED);
+    if (cached > 0) return cached;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    __atomic_store_n(&g_sm_count[dev], n, __ATOMIC_RELAXED);
+    return n;
 }
 
 int cluster_size() {

@@ -42,7 +42,23 @@ long long launches();
 
 // Requires a device of compute capability 10.x (the kernels are sm_100a-only).
 int require_sm100();
-int sm_count();
+int sm_count();      // of the CURRENT device (cached per device)
+
+// "Done once per DEVICE" flag for per-device function attributes (the dynamic shared-memory opt-in of
+// cudaFuncSetAttribute is per device: a process-wide `static bool` left every kernel above 48 KB unlaunchable
+// on the second GPU of a process).  need() is true the first time it is called with a given current device;
+// a race between host threads only sets the attribute twice.
+struct DeviceOnce {
+    static constexpr int kMaxDevices = 64;
+    unsigned char done[kMaxDevices] = {};
+    bool need() {
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;
+        if (__atomic_load_n(&done[dev], __ATOMIC_RELAXED)) return false;
+        __atomic_store_n(&done[dev], static_cast<unsigned char>(1), __ATOMIC_RELAXED);
+        return true;
+    }
+};
 
 // 2-D bf16 tensor map: `rows` x `cols` elements, row pitch `ld` elements, box = box_rows x 64
 // elements (128 B) with the 128-byte swizzle the UMMA descriptors expect; OOB reads give zeros.

@@ -94,7 +94,7 @@ static int pack_all(const WLayout& L, const float* const* p, uint8_t* dst, cudaS
 
 // workspace carve-up (all 256-byte aligned)
 struct WsLayout {
-    size_t off, n_tok, owner, x, h, big, q0, a0, u0, total;
+    size_t off, n_tok, owner, x, h, big, q0, a0, u0, ffn, ffn_bytes, total;
     int t_max, big_ld;
 };
 static WsLayout make_ws(const ofx_shape* s, int batch) {
@@ -115,6 +115,9 @@ static WsLayout make_ws(const ofx_shape* s, int batch) {
     W.q0 = take(static_cast<size_t>(batch) * dm * esz);
     W.a0 = take(static_cast<size_t>(batch) * dm * esz);
     W.u0 = take(static_cast<size_t>(batch) * fp * esz);
+    // the fused FFN block's exchange ring + counters (bf16 path, d_model 512)
+    W.ffn_bytes = (s->precision == OFX_PREC_BF16 && ffn_block_supported(s->d_model, static_cast<int>(fp))) ? ffn_block_workspace_bytes() : 0;
+    W.ffn = take(W.ffn_bytes);
     W.total = o;
     return W;
 }
@@ -199,6 +202,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
                 FfnBlockArgs fa{x, W.t_max, n_tok, dm, fp, lf(l, L.ln2w), lf(l, L.ln2b), lw(l, L.w_1),
                                 lf(l, L.b_1), lw(l, L.w_2), lf(l, L.b_2)};
                 if (ffn_emits_ln()) { fa.h_next = h; fa.lnn_w = lf(l + 1, L.ln1w); fa.lnn_b = lf(l + 1, L.ln1b); }
+                fa.workspace = ws + W.ffn; fa.workspace_bytes = W.ffn_bytes;
                 OFX_TRY(ffn_block_bf16(fa, st));
             } else {
                 OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
@@ -224,6 +228,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
             if (fused_ffn) {
                 FfnBlockArgs fa{x, B, nullptr, dm, fp, lf(l, L.ln2w), lf(l, L.ln2b), lw(l, L.w_1),
                                 lf(l, L.b_1), lw(l, L.w_2), lf(l, L.b_2)};
+                fa.workspace = ws + W.ffn; fa.workspace_bytes = W.ffn_bytes;
                 OFX_TRY(ffn_block_bf16(fa, st));
             } else {
                 OFX_TRY(layernorm<T>(x, B, nullptr, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
@@ -324,28 +329,6 @@ int ofx_fuse(const float* img, const float* txt, int64_t rows, int32_t dpm, int3
     return fuse_rows(img, txt, rows, dpm, mode, normalize, out, static_cast<cudaStream_t>(stream));
 }
 
-int ofx_fetch_valid_items(const float* host_img, const float* host_txt, const uint8_t* mask, int32_t batch,
-                          int32_t max_items, int32_t dpm, float* dev_img, float* dev_txt, void* stream) {
-    if (batch < 0 || max_items < 1) return fail(OFX_E_SHAPE, "ofx_fetch_valid_items: batch %d, max_items %d", batch, max_items);
-    if (dpm < 4 || dpm % 4) return fail(OFX_E_SHAPE, "ofx_fetch_valid_items: dim_per_modality %d must be a multiple of 4", dpm);
-    if (batch == 0) return OFX_OK;
-    if (!host_img || !host_txt || !mask || !dev_img || !dev_txt) return fail(OFX_E_ARG, "ofx_fetch_valid_items: null argument");
-    if ((reinterpret_cast<uintptr_t>(host_img) | reinterpret_cast<uintptr_t>(host_txt) |
-         reinterpret_cast<uintptr_t>(dev_img) | reinterpret_cast<uintptr_t>(dev_txt)) % 16)
-        return fail(OFX_E_ARG, "ofx_fetch_valid_items: misaligned pointer");
-    OFX_TRY(require_sm100());
-    // the source must be page-locked host memory (or device memory): pageable memory is not addressable by the SMs
-    for (const float* ptr : {host_img, host_txt}) {
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess || at.type == cudaMemoryTypeUnregistered) {
-            cudaGetLastError();
-            return fail(OFX_E_ARG, "ofx_fetch_valid_items: source is not pinned host memory (use tensor.pin_memory())");
-        }
-    }
-    return fetch_valid(host_img, host_txt, mask, static_cast<long long>(batch) * max_items, dpm, dev_img, dev_txt,
-                       static_cast<cudaStream_t>(stream));
-}
-
 int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int32_t m, int32_t n, int32_t k,
                   const float* bias, int32_t act_mish, const float* residual, int64_t ldr, void* out,
                   int64_t ldo, int32_t out_f32, void* stream) {
@@ -355,21 +338,28 @@ int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int32_
     return gemm_bf16(g, static_cast<cudaStream_t>(stream));
 }
 
+size_t ofx_ffn_block_workspace_bytes(int32_t rows, int32_t d_model, int32_t d_ffn_padded) {
+    if (rows < 0 || !ffn_block_supported(d_model, d_ffn_padded)) return 0;
+    return ffn_block_workspace_bytes();
+}
+
 int ofx_ffn_block_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_padded, const float* ln_w,
                        const float* ln_b, const void* w1, const float* b1, const void* w2, const float* b2,
-                       void* stream) {
+                       void* workspace, size_t workspace_bytes, void* stream) {
     if (!x || !ln_w || !ln_b || !w1 || !b1 || !w2 || !b2) return fail(OFX_E_ARG, "ofx_ffn_block_bf16: null argument");
     if (rows < 0) return fail(OFX_E_SHAPE, "ofx_ffn_block_bf16: rows %d", rows);
     if (!ffn_block_supported(d_model, d_ffn_padded))
         return fail(OFX_E_SHAPE, "ofx_ffn_block_bf16: needs d_model 512 and d_ffn_padded %% 256 == 0");
     OFX_TRY(require_sm100());
     FfnBlockArgs fa{x, rows, nullptr, d_model, d_ffn_padded, ln_w, ln_b, w1, b1, w2, b2};
+    fa.workspace = workspace; fa.workspace_bytes = workspace_bytes;
     return ffn_block_bf16(fa, static_cast<cudaStream_t>(stream));
 }
 
 int ofx_ffn_block_ln_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn_padded, const float* ln_w,
                           const float* ln_b, const void* w1, const float* b1, const void* w2, const float* b2,
-                          void* h_next, const float* next_ln_w, const float* next_ln_b, void* stream) {
+                          void* h_next, const float* next_ln_w, const float* next_ln_b, void* workspace,
+                          size_t workspace_bytes, void* stream) {
     if (!x || !ln_w || !ln_b || !w1 || !b1 || !w2 || !b2 || !h_next || !next_ln_w || !next_ln_b)
         return fail(OFX_E_ARG, "ofx_ffn_block_ln_bf16: null argument");
     if (rows < 0) return fail(OFX_E_SHAPE, "ofx_ffn_block_ln_bf16: rows %d", rows);
@@ -379,6 +369,7 @@ int ofx_ffn_block_ln_bf16(float* x, int32_t rows, int32_t d_model, int32_t d_ffn
     OFX_TRY(require_sm100());
     FfnBlockArgs fa{x, rows, nullptr, d_model, d_ffn_padded, ln_w, ln_b, w1, b1, w2, b2};
     fa.h_next = h_next; fa.lnn_w = next_ln_w; fa.lnn_b = next_ln_b;
+    fa.workspace = workspace; fa.workspace_bytes = workspace_bytes;
     return ffn_block_bf16(fa, static_cast<cudaStream_t>(stream));
 }
 }

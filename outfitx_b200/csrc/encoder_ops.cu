@@ -291,51 +291,6 @@ int scan_valid(const uint8_t* mask, int batch, int max_items, int* off, int* n_t
     return OFX_OK;
 }
 
-// ------------------------------------------------------------------ host -> device fetch of the valid slots
-// The reference moves every collated batch to the GPU whole (`v.to(local_rank)`,
-// compatibility_prediction_trainer.py:140-145): (B, 16, dpm) fp32 per modality, padded slots
-// included -- 44 % of the bytes when n ~ U{2..16}.  Here the SMs read the PINNED host tensors directly
-// (unified addressing: the host pointer is valid on the device) and fetch only the slots the mask marks
-// valid; padded slots of the device copy are left untouched (no kernel of the path reads them).
-// One warp per (outfit, slot): 8 independent 16-byte loads per lane are in flight before the first store,
-// and with thousands of warps resident the PCIe read queue stays full.
-__global__ void __launch_bounds__(256)
-fetch_valid_kernel(const float* __restrict__ h_img, const float* __restrict__ h_txt, const uint8_t* __restrict__ mask,
-                   long long n_slots, int dpm, float* __restrict__ d_img, float* __restrict__ d_txt) {
-    const long long slot = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-    if (slot >= n_slots || mask[slot]) return;
-    const int lane = threadIdx.x & 31;
-    const long long base = slot * dpm;
-    for (int c = lane * 4; c < dpm; c += 512) {
-        float4 a[4], b[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int cc = c + u * 128;
-            if (cc < dpm) {
-                a[u] = __ldcs(reinterpret_cast<const float4*>(h_img + base + cc));
-                b[u] = __ldcs(reinterpret_cast<const float4*>(h_txt + base + cc));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int cc = c + u * 128;
-            if (cc < dpm) {
-                *reinterpret_cast<float4*>(d_img + base + cc) = a[u];
-                *reinterpret_cast<float4*>(d_txt + base + cc) = b[u];
-            }
-        }
-    }
-}
-
-int fetch_valid(const float* h_img, const float* h_txt, const uint8_t* mask, long long n_slots, int dpm,
-                float* d_img, float* d_txt, cudaStream_t stream) {
-    if (n_slots <= 0) return OFX_OK;
-    fetch_valid_kernel<<<static_cast<unsigned>((n_slots + 7) / 8), 256, 0, stream>>>(h_img, h_txt, mask, n_slots, dpm,
-                                                                                  d_img, d_txt);
-    OFX_LAUNCH_CHECK();
-    return OFX_OK;
-}
-
 // ------------------------------------------------------------------ LayerNorm: one warp per row
 template <int DM, class T>
 __global__ void __launch_bounds__(256)
@@ -759,10 +714,9 @@ attention_mma_kernel(const AttnArgs a) {
 template <int HD, int NSPLIT>
 static int launch_attention_mma_split(const AttnArgs& a, cudaStream_t stream) {
     constexpr int smem = (3 * kAttnMaxS + 1) * (16 * HD / NSPLIT + 8) * 2;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         OFX_CUDA(cudaFuncSetAttribute(attention_mma_kernel<HD, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     static int small_ok = -1;    // OFX_ATTN_SMALL=0: no S <= 8 specialisation (A/B timing)
     if (small_ok < 0) { const char* e = getenv("OFX_ATTN_SMALL"); small_ok = (e && e[0] == '0') ? 0 : 1; }

@@ -616,20 +616,38 @@ ffn_block_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
 
 bool ffn_block_supported(int dm, int fp) { return dm == ffnb::DM && fp > 0 && fp % ffnb::CH == 0; }
 
+// OFX_FFN_V1=1 selects the round-1 kernel (A/B timing; results agree to the last bf16 rounding)
+static bool use_v1() {
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("OFX_FFN_V1"); v1 = (e && e[0] == '1') ? 1 : 0; }
+    return v1 == 1;
+}
+size_t ffn_block_workspace_bytes() { return ffn_block2_workspace_bytes(sm_count()); }
+
 int ffn_block_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
+    if (!use_v1() && ffn_block2_supported(a.dm, a.fp)) return ffn_block2_bf16(a, stream);
+    return ffn_block1_bf16(a, stream);
+}
+
+int ffn_block1_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
     using namespace ffnb;
     if (a.rows <= 0) return OFX_OK;
     if (a.dm != DM || a.fp <= 0 || a.fp % CH != 0)
         return fail(OFX_E_SHAPE, "ffn_block: needs d_model 512 and padded d_ffn %% 256 == 0 (got %d, %d)", a.dm, a.fp);
     CUtensorMap tm_w1, tm_w2;
+    // OFX_FFN_DEBUG (timing experiments: bits 1 / 256 / 512 give WRONG results, bit 8 allocates and synchronises)
+    // exists only in instrumented builds (-DOFX_DEBUG); the product library cannot be switched into either.
+#ifdef OFX_DEBUG
     static int debug = -1;
     if (debug < 0) { const char* e = getenv("OFX_FFN_DEBUG"); debug = e ? atoi(e) : 0; }
+#else
+    constexpr int debug = 0;
+#endif
     OFX_TRY(make_tmap_bf16(&tm_w1, a.w1, static_cast<uint64_t>(a.fp), DM, DM, 128));
     OFX_TRY(make_tmap_bf16(&tm_w2, a.w2, DM, static_cast<uint64_t>(a.fp), a.fp, 128));
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         OFX_CUDA(cudaFuncSetAttribute(ffn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
     }
     const int n_tiles = (a.rows + TILE - 1) / TILE;
     const int max_pairs = sm_count() / 2;

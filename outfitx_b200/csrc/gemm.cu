@@ -352,10 +352,9 @@ static int launch_tc(const GemmArgs& g, cudaStream_t stream) {
     constexpr bool kPair = CL == 2;    // the linear layers run as CTA pairs (QKV: 116 -> 102 us at 82k tokens)
     auto kern = tc_kernel<BN, kStages, CL, SchedGemm, Epi, kPair>;
     constexpr int smem = tc_smem_bytes<BN, kStages, Epi, kPair>();
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    static DeviceOnce configured;  // per instantiation
+    if (configured.need()) {
         OFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     const int m_groups = ((g.m + kBM - 1) / kBM + CL - 1) / CL;
     const int tiles = m_groups * (g.n / BN);
@@ -374,6 +373,10 @@ static int launch_tc(const GemmArgs& g, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
+    // Role instrumentation (OFX_TC_PROF=1) allocates and synchronises, which the C ABI promises never to do:
+    // it exists only in instrumented builds (python -m outfitx_b200.build --debug -> -DOFX_DEBUG, loaded
+    // through OFX_LIB_PATH), never in the product library.
+#ifdef OFX_DEBUG
     static int prof_on = -1;
     static long long* prof_dev = nullptr;
     if (prof_on < 0) { const char* e = getenv("OFX_TC_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
@@ -382,6 +385,10 @@ static int launch_tc(const GemmArgs& g, cudaStream_t stream) {
         OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 256, stream));
         OFX_CUDA(cudaMemcpyToSymbolAsync(g_tc_prof, &prof_dev, sizeof(prof_dev), 0, cudaMemcpyHostToDevice, stream));
     }
+#else
+    constexpr int prof_on = 0;
+    long long* const prof_dev = nullptr;
+#endif
     OFX_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, sp, ep, g.k / kBK));
     if (prof_on) {
         long long h[8 * 256];

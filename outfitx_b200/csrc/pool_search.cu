@@ -105,11 +105,10 @@ extern "C" int ofx_pool_search(const float* pools, const int64_t* pool_offsets, 
         return fail(OFX_E_ARG, "ofx_pool_search: misaligned pointer");
     OFX_TRY(require_sm100());
     const size_t smem = (sizeof(double) + sizeof(int)) * kPoolMax + sizeof(float) * dim;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         OFX_CUDA(cudaFuncSetAttribute(pool_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>((sizeof(double) + sizeof(int)) * kPoolMax + sizeof(float) * 2048)));
-        configured = true;
     }
     pool_search_kernel<<<n_query, kPoolThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         pools, reinterpret_cast<const long long*>(pool_offsets), queries, query_pool, dim, k, metric,

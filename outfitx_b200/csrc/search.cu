@@ -418,7 +418,8 @@ to_bf16_kernel(const float* __restrict__ in, int n_query, int dim, float aug, __
 
 __global__ void __launch_bounds__(256)
 gallery_pack_kernel(const float* __restrict__ g, long long n_rows, int dim,
-                    __nv_bfloat16* __restrict__ out, float* __restrict__ half_sqnorm) {
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ half_sqnorm,
+                    unsigned int* __restrict__ max_hs_bits) {
     const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const int lane = threadIdx.x & 31;
@@ -435,7 +436,10 @@ gallery_pack_kernel(const float* __restrict__ g, long long n_rows, int dim,
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) half_sqnorm[row] = 0.5f * ss;
+    if (lane == 0) {
+        half_sqnorm[row] = 0.5f * ss;
+        atomicMax(max_hs_bits, __float_as_uint(0.5f * ss));     // non-negative floats order like their bit patterns
+    }
     // bias columns: -0.5|g|^2 = hi + lo in bf16, then zeros (2 x 4 bytes per lane = 64 columns)
     const float bias = -0.5f * ss;
     const __nv_bfloat16 hi = __float2bfloat16_rn(bias);
@@ -462,26 +466,44 @@ struct MergeArgs {
     double* out_score;          // (nq, k)
     long long* out_idx;         // (nq, k)
     const uint32_t* thr_enc;    // per-query encoded threshold left by pass 1 (<= the global kcap-th best)
+    const float* max_half_sqnorm;   // max over the shard of 0.5|g|^2 (tail of the packed gallery), for the certificate
+    unsigned char* certified;   // (nq) or nullptr: 1 = the returned top-k is PROVEN equal to the exhaustive fp64 result
     unsigned long long* prof;   // OFX_MERGE_PROF=1: [0..3] summed cycles of gather / sort / re-score / rank, [4] CTAs that sorted all keys
 };
 
 constexpr int kMergeThreads = 256;
 constexpr int kMergeSmall = 512;   // capacity of the selected-key buffer (power of two)
 constexpr int kMergeSelect = 128;  // with more candidates than this, select before sorting
-constexpr int kMaxRerank = 64;
+constexpr int kMaxRerank = 128;
+constexpr int kMaxScored = kMaxRerank + kMergeSmall;   // shortlist + certificate extension
+
+// Rigorous bound on |bf16-pass score - exact score| of ANY gallery row for a query of norm qn, G = max |g|:
+//   operands rounded to bf16 (round to nearest, relative error u = 2^-9 each): |q.g - q^.g^| <= (2u + u^2) |q||g|;
+//   fp32 accumulation of the K = dim + 64 exact bf16 products in the tensor core: <= K 2^-22 |q^||g^| (truncating
+//   adder, factor-two margin);  the L2 bias -0.5|g|^2 as bf16 hi + lo of an fp32 sum: <= (2^-18 + dim 2^-24) 0.5 G^2.
+// The certificate below is a worst-case statement; the typical error is ~50x smaller (it grows with sqrt(K), not K).
+__device__ __forceinline__ double bf16_score_error_bound(double qn, double half_g2, int dim, int metric) {
+    const double u = 1.0 / 512.0;
+    const double g = sqrt(2.0 * half_g2);
+    double e = (2.0 * u + u * u + (dim + 64) * (1.0 / 4194304.0)) * qn * g * (1.0 + u) * (1.0 + u);
+    if (metric == OFX_METRIC_L2) e += (1.0 / 262144.0 + dim * (1.0 / 16777216.0)) * half_g2;
+    return e * 1.01;
+}
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_rerank_kernel(const MergeArgs a) {
     extern __shared__ unsigned long long keys[];
-    __shared__ double r_score[kMaxRerank];
-    __shared__ long long r_idx[kMaxRerank];
+    __shared__ double r_score[kMaxScored];
+    __shared__ long long r_idx[kMaxScored];
     __shared__ int n_valid;
+    __shared__ int n_ext;
+    __shared__ double s_kth, s_qq;
     const int q = blockIdx.x, tid = threadIdx.x;
     const int qb = q / kBM, r = q % kBM;
     __shared__ int n_small, sel_bin;
     __shared__ unsigned int es_lo, es_hi;
     __shared__ int hist[256];
-    if (tid == 0) { n_valid = 0; n_small = 0; es_lo = 0xFFFFFFFFu; es_hi = 0u; sel_bin = -1; }
+    if (tid == 0) { n_valid = 0; n_small = 0; es_lo = 0xFFFFFFFFu; es_hi = 0u; sel_bin = -1; n_ext = 0; s_qq = 0.0; }
     hist[tid] = 0;     // kMergeThreads == 256
     __syncthreads();
     const long long tstart = a.prof ? clock64() : 0;
@@ -584,10 +606,13 @@ merge_rerank_kernel(const MergeArgs a) {
         }
     }
     if (a.prof && tid == 0) { tp2 = clock64(); atomicAdd(a.prof + 1, static_cast<unsigned long long>(tp2 - tp1)); }
+    const int n_total = n_valid;      // every candidate pass 1 kept for this query (all of them are still in keys[])
+    __syncthreads();
     if (use_small && tid == 0) n_valid = n_small;
     __syncthreads();
     const int n_r = min(min(n_valid, a.kcap), kMaxRerank);
     const int warp = tid >> 5, lane = tid & 31;
+    const unsigned long long key_last = n_r > 0 ? sk[n_r - 1] : 0ull;   // worst (bf16 score, index) of the shortlist
     // the gallery rows of the candidates are cold 4 KB reads scattered over HBM: every warp asks for all of its
     // rows at once (one 128-byte line per lane and row) before it starts on the first
     if (a.gallery_f32) {
@@ -598,62 +623,128 @@ merge_rerank_kernel(const MergeArgs a) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(g + d));
         }
     }
+    // exact score of one candidate (whole warp), fp64 from the fp32 rows
+    auto exact_score = [&](unsigned long long key, long long idx) -> double {
+        if (!a.gallery_f32) return static_cast<double>(dec_score(static_cast<uint32_t>(key >> 32)));
+        const float* g = a.gallery_f32 + idx * a.dim;
+        const float* qv = a.queries + static_cast<long long>(q) * a.dim;
+        double acc = 0.0, nn = 0.0;
+        // eight gallery elements per lane in flight (the row is a cold 4 KB read from HBM; as a rolled loop
+        // its 32 iterations were 32 exposed round trips); same element order per lane as before
+        for (int d0 = lane; d0 < a.dim; d0 += 256) {
+            float gv[8], qq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int d = d0 + 32 * u;
+                gv[u] = d < a.dim ? __ldcs(g + d) : 0.f;
+                qq[u] = d < a.dim ? __ldg(qv + d) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double gd = static_cast<double>(gv[u]);
+                acc = fma(static_cast<double>(qq[u]), gd, acc);
+                nn = fma(gd, gd, nn);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        }
+        return a.metric == OFX_METRIC_L2 ? acc - 0.5 * nn : acc;
+    };
     for (int c = warp; c < n_r; c += kMergeThreads / 32) {
         const unsigned long long key = sk[c];
         const long long idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
-        double score;
-        if (a.gallery_f32) {
-            const float* g = a.gallery_f32 + idx * a.dim;
-            const float* qv = a.queries + static_cast<long long>(q) * a.dim;
-            double acc = 0.0, nn = 0.0;
-            // eight gallery elements per lane in flight (the row is a cold 4 KB read from HBM; as a rolled loop
-            // its 32 iterations were 32 exposed round trips); same element order per lane as before
-            for (int d0 = lane; d0 < a.dim; d0 += 256) {
-                float gv[8], qq[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int d = d0 + 32 * u;
-                    gv[u] = d < a.dim ? __ldcs(g + d) : 0.f;
-                    qq[u] = d < a.dim ? __ldg(qv + d) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const double gd = static_cast<double>(gv[u]);
-                    acc = fma(static_cast<double>(qq[u]), gd, acc);
-                    nn = fma(gd, gd, nn);
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                nn += __shfl_xor_sync(0xffffffffu, nn, o);
-            }
-            score = a.metric == OFX_METRIC_L2 ? acc - 0.5 * nn : acc;
-        } else {
-            score = static_cast<double>(dec_score(static_cast<uint32_t>(key >> 32)));
-        }
+        const double score = exact_score(key, idx);
         if (lane == 0) { r_score[c] = score; r_idx[c] = idx; }
+    }
+    // |q|^2 for the certificate (fp64, all threads)
+    if (a.certified && a.gallery_f32) {
+        double qq = 0.0;
+        for (int d = tid; d < a.dim; d += kMergeThreads) {
+            const double v = static_cast<double>(__ldg(a.queries + static_cast<long long>(q) * a.dim + d));
+            qq = fma(v, v, qq);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+        if (lane == 0) atomicAdd(&s_qq, qq);
     }
     __syncthreads();
     if (a.prof && tid == 0) { tp0 = clock64(); atomicAdd(a.prof + 2, static_cast<unsigned long long>(tp0 - tp2)); }
-    if (tid < a.k) {
-        const long long o = static_cast<long long>(q) * a.k + tid;
-        if (tid >= n_r) { a.out_score[o] = -INFINITY; a.out_idx[o] = -1; }
-    }
-    if (tid < n_r) {
-        const double s = r_score[tid];
-        const long long id = r_idx[tid];
-        int rank = 0;
-        for (int j = 0; j < n_r; ++j) {
-            const double sj = r_score[j];
-            rank += (sj > s) || (sj == s && r_idx[j] < id);
+    // rank of every scored candidate under (score desc, index asc); rank k-1 is the k-th best
+    auto rank_and_emit = [&](int n_s) {
+        if (tid == 0) s_kth = -INFINITY;
+        __syncthreads();
+        if (tid < a.k && tid >= n_s) {
+            const long long o = static_cast<long long>(q) * a.k + tid;
+            a.out_score[o] = -INFINITY; a.out_idx[o] = -1;
         }
-        if (rank < a.k) {
-            const long long o = static_cast<long long>(q) * a.k + rank;
-            a.out_score[o] = s;
-            a.out_idx[o] = a.id_offset + id;
+        for (int e = tid; e < n_s; e += kMergeThreads) {
+            const double se = r_score[e];
+            const long long id = r_idx[e];
+            int rank = 0;
+            for (int j = 0; j < n_s; ++j) {
+                const double sj = r_score[j];
+                rank += (sj > se) || (sj == se && r_idx[j] < id);
+            }
+            if (rank < a.k) {
+                const long long o = static_cast<long long>(q) * a.k + rank;
+                a.out_score[o] = se;
+                a.out_idx[o] = a.id_offset + id;
+                if (rank == a.k - 1) s_kth = se;
+            }
+        }
+        __syncthreads();
+    };
+    rank_and_emit(n_r);
+    if (!a.certified) return;
+    // ---------------------------------------------------------------- exactness certificate
+    // Claim to prove: no gallery row outside the scored set can reach the k-th best exact score S_k.
+    //  * rows pass 1 never listed: their bf16 score is <= the final per-query threshold T_out (a unit drops a row
+    //    only below its admission gate, and every gate -- seeded bound, a finished unit's list minimum -- is folded
+    //    into thr_enc with atomicMax), so their exact score is <= T_out + eps;
+    //  * listed rows outside the shortlist: bf16 score <= the shortlist's worst, T_in.  If S_k - eps does not clear
+    //    T_in, every listed row with bf16 score >= S_k - eps is re-scored too (the extension below).
+    // eps = bf16_score_error_bound(|q|, max 0.5|g|^2).  No re-rank (bf16 ranking requested): nothing is claimed.
+    if (!a.gallery_f32) { if (tid == 0) a.certified[q] = 0; return; }
+    const double eps = bf16_score_error_bound(sqrt(s_qq), static_cast<double>(__ldg(a.max_half_sqnorm)), a.dim, a.metric);
+    const uint32_t thr_e = a.thr_enc ? __ldcg(a.thr_enc + q) : 0u;
+    const bool gated = thr_e != 0u;                  // some row may have been dropped without being listed
+    const double t_out = gated ? static_cast<double>(dec_score(thr_e)) : -INFINITY;
+    bool ok = true;
+    int n_s = n_r;
+    if (n_total > n_r) {
+        const double need = s_kth - eps;             // -inf when fewer than k rows were scored: everything listed is needed
+        const double t_in = static_cast<double>(dec_score(static_cast<uint32_t>(key_last >> 32)));
+        if (!(t_in < need)) {
+            // extension: listed candidates below the shortlist whose bf16 score reaches `need` (keys[] still holds
+            // every listed candidate; the shortlist is exactly the keys >= key_last)
+            for (int e = tid; e < a.n_pad; e += kMergeThreads) {
+                const unsigned long long key = keys[e];
+                if (key && key < key_last && static_cast<double>(dec_score(static_cast<uint32_t>(key >> 32))) >= need) {
+                    const int pos = atomicAdd(&n_ext, 1);
+                    if (pos < kMergeSmall) r_idx[n_r + pos] = static_cast<long long>(key);   // parked, replaced by the index below
+                }
+            }
+            __syncthreads();
+            if (n_ext > kMergeSmall) ok = false;     // more near-ties than the extension holds: leave it to the exhaustive fallback
+            const int n_e = min(n_ext, kMergeSmall);
+            for (int c = warp; c < n_e; c += kMergeThreads / 32) {
+                const unsigned long long key = static_cast<unsigned long long>(r_idx[n_r + c]);
+                const long long idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+                const double score = exact_score(key, idx);
+                __syncwarp();
+                if (lane == 0) { r_score[n_r + c] = score; r_idx[n_r + c] = idx; }
+            }
+            __syncthreads();
+            n_s = n_r + n_e;
+            rank_and_emit(n_s);
         }
     }
+    if (n_s < a.k) ok = ok && !gated && n_total == n_s;        // fewer than k rows: exact only if nothing was ever dropped
+    else if (gated) ok = ok && (t_out < s_kth - eps);
+    if (tid == 0) a.certified[q] = ok ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -661,12 +752,14 @@ merge_rerank_kernel(const MergeArgs a) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 topk_merge_kernel(const double* __restrict__ scores, const long long* __restrict__ idx, int n_lists,
-                  int n_query, int k, double* __restrict__ out_score, long long* __restrict__ out_idx) {
+                  int n_query, int k, double* __restrict__ out_score, long long* __restrict__ out_idx,
+                  const int* __restrict__ out_row = nullptr) {
     extern __shared__ unsigned char sm[];
     const int n = n_lists * k;
     double* s = reinterpret_cast<double*>(sm);
     long long* id = reinterpret_cast<long long*>(sm + sizeof(double) * n);
     const int q = blockIdx.x;
+    const long long oq = out_row ? out_row[q] : q;      // the exhaustive fallback scatters into the caller's rows
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         const int l = e / k, j = e - l * k;
         const long long src = (static_cast<long long>(l) * n_query + q) * k + j;
@@ -688,22 +781,137 @@ topk_merge_kernel(const double* __restrict__ scores, const long long* __restrict
             rank += better;
         }
         if (rank < k) {
-            out_score[static_cast<long long>(q) * k + rank] = pad_e ? -INFINITY : se;
-            out_idx[static_cast<long long>(q) * k + rank] = pad_e ? -1 : ie;
+            out_score[oq * k + rank] = pad_e ? -INFINITY : se;
+            out_idx[oq * k + rank] = pad_e ? -1 : ie;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Exhaustive fp64 search of a few selected queries: the fallback for queries whose tensor-core result could not
+// be certified (near-duplicate gallery rows closer than bf16 resolution, ofx_topk_search's out_certified == 0).
+// CTA (c, s): row chunk c x group s of up to kExactQ selected queries.  A warp takes one gallery row at a time
+// (coalesced 16-byte loads), forms the fp64 dot products with the group's queries (fp32 copies in shared memory)
+// and keeps a private top-k per query; the CTA merges its 8 warps' lists and emits one list per (chunk, query);
+// topk_merge_kernel then merges the chunks.  Arithmetic and ranking are those of merge_rerank_kernel / the fp64
+// oracle: score = q.g (- 0.5 |g|^2), ties to the lowest index.
+// ---------------------------------------------------------------------------------------
+constexpr int kExactQ = 8;
+constexpr int kExactWarps = 8;
+
+__global__ void __launch_bounds__(kExactWarps * 32)
+exact_scan_kernel(const float* __restrict__ gallery, long long n_rows, int dim, int metric,
+                  const float* __restrict__ queries, const int* __restrict__ sel, int n_sel, int k,
+                  long long rows_per_chunk, double* __restrict__ part_s, long long* __restrict__ part_i) {
+    extern __shared__ unsigned char sm_raw[];
+    float* sq = reinterpret_cast<float*>(sm_raw);                                   // [kExactQ][dim]
+    double* ls = reinterpret_cast<double*>(sm_raw + sizeof(float) * kExactQ * dim);  // [warps][kExactQ][k]
+    long long* li = reinterpret_cast<long long*>(ls + kExactWarps * kExactQ * k);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.y * kExactQ, nq = min(kExactQ, n_sel - q0);
+    for (int e = threadIdx.x; e < nq * dim; e += blockDim.x)
+        sq[e] = queries[static_cast<long long>(sel[q0 + e / dim]) * dim + e % dim];
+    for (int e = threadIdx.x; e < kExactWarps * kExactQ * k; e += blockDim.x) { ls[e] = -INFINITY; li[e] = -1; }
+    __syncthreads();
+    double* my_s = ls + warp * kExactQ * k;
+    long long* my_i = li + warp * kExactQ * k;
+    double worst_s[kExactQ];      // current worst entry of each private list (lane 0's copy is authoritative)
+    int worst_p[kExactQ];
+#pragma unroll
+    for (int j = 0; j < kExactQ; ++j) { worst_s[j] = -INFINITY; worst_p[j] = 0; }
+    const long long lo = blockIdx.x * rows_per_chunk, hi = min(n_rows, lo + rows_per_chunk);
+    for (long long row = lo + warp; row < hi; row += kExactWarps) {
+        double acc[kExactQ], nn = 0.0;
+#pragma unroll
+        for (int j = 0; j < kExactQ; ++j) acc[j] = 0.0;
+        for (int d = lane * 4; d < dim; d += 128) {
+            const float4 g4 = __ldcs(reinterpret_cast<const float4*>(gallery + row * dim + d));
+            const double g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nn = fma(g[u], g[u], nn);
+#pragma unroll
+            for (int j = 0; j < kExactQ; ++j) {
+                if (j < nq) {
+                    const float4 q4 = *reinterpret_cast<const float4*>(sq + j * dim + d);
+                    acc[j] = fma(static_cast<double>(q4.x), g[0], acc[j]);
+                    acc[j] = fma(static_cast<double>(q4.y), g[1], acc[j]);
+                    acc[j] = fma(static_cast<double>(q4.z), g[2], acc[j]);
+                    acc[j] = fma(static_cast<double>(q4.w), g[3], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nn += __shfl_xor_sync(0xffffffffu, nn, o);
+#pragma unroll
+            for (int j = 0; j < kExactQ; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < kExactQ; ++j) {
+                if (j >= nq) continue;
+                const double sc = metric == OFX_METRIC_L2 ? acc[j] - 0.5 * nn : acc[j];
+                // rows arrive in ascending index order, so an equal score never displaces an earlier row
+                if (sc > worst_s[j] || my_i[j * k + worst_p[j]] < 0) {
+                    my_s[j * k + worst_p[j]] = sc;
+                    my_i[j * k + worst_p[j]] = row;
+                    double ws = my_s[j * k]; long long wi = my_i[j * k]; int wp = 0;
+                    for (int t = 1; t < k; ++t) {
+                        const double st = my_s[j * k + t]; const long long it = my_i[j * k + t];
+                        // worst = an empty slot first, else lowest score, among equals the highest index
+                        const bool worse = (wi >= 0) && (it < 0 || st < ws || (st == ws && it > wi));
+                        if (worse) { ws = st; wi = it; wp = t; }
+                    }
+                    worst_s[j] = wi < 0 ? -INFINITY : ws;
+                    worst_p[j] = wp;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // merge the warps' lists: rank by counting over kExactWarps * k entries per query
+    const int n = kExactWarps * k;
+    for (int e = threadIdx.x; e < nq * n; e += blockDim.x) {
+        const int j = e / n, t = e % n, w = t / k, p = t % k;
+        const double se = ls[(w * kExactQ + j) * k + p];
+        const long long ie = li[(w * kExactQ + j) * k + p];
+        if (ie < 0) continue;
+        int rank = 0;
+        for (int w2 = 0; w2 < kExactWarps; ++w2)
+            for (int p2 = 0; p2 < k; ++p2) {
+                const long long i2 = li[(w2 * kExactQ + j) * k + p2];
+                if (i2 < 0) continue;
+                const double s2 = ls[(w2 * kExactQ + j) * k + p2];
+                rank += (s2 > se) || (s2 == se && i2 < ie);
+            }
+        if (rank < k) {
+            const long long o = (static_cast<long long>(blockIdx.x) * n_sel + q0 + j) * k + rank;
+            part_s[o] = se;
+            part_i[o] = ie;
+        }
+    }
+}
+
+__global__ void add_offset_kernel(long long* idx, const int* __restrict__ sel, int n_sel, int k, long long offset,
+                                  unsigned char* certified) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_sel * k) return;
+    const long long o = static_cast<long long>(sel[e / k]) * k + e % k;
+    if (idx[o] >= 0) idx[o] += offset;
+    if (certified && e % k == 0) certified[sel[e / k]] = 1;
 }
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 struct PackedGallery {
-    size_t rows_bytes, total;
+    size_t rows_bytes, stats, total;
 };
 static PackedGallery gallery_layout(long long n_rows, int dim) {
     PackedGallery g{};
     g.rows_bytes = align_up(static_cast<size_t>(n_rows) * (dim + kAugCols) * 2, 256);
-    g.total = g.rows_bytes + align_up(static_cast<size_t>(n_rows) * 4, 256);
+    g.stats = g.rows_bytes + align_up(static_cast<size_t>(n_rows) * 4, 256);
+    g.total = g.stats + 256;      // [0] max over the shard of 0.5|g|^2 (fp32), for the exactness certificate
     return g;
 }
 
@@ -712,7 +920,11 @@ struct SearchWs {
     int kcap;
     SearchPlan plan;
 };
-static int kcap_for(int k) { return k <= 16 ? 32 : 64; }
+// List capacity of pass 1.  The certificate needs the k-th best EXACT score to clear the kcap-th best bf16 score by
+// the worst-case bf16 error (~0.13 sigma of the score distribution at dim 1024); in the far tail of 10 M rows that
+// takes kcap >= ~2 k, hence the generous steps.  k <= 12 keeps the 32-entry lists of the headline top-10 search.
+static int kcap_for(int k) { return k <= 12 ? 32 : (k <= 25 ? 64 : 128); }
+constexpr int kMaxK = 64;
 
 static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     SearchWs w{};
@@ -742,10 +954,9 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     auto kern = tc_kernel<kSearchBN, STAGES, CL, SchedSearch, Epi, PAIR>;   // CL = 2: multicast cluster or CTA pair
     constexpr int smem = tc_smem_bytes<kSearchBN, STAGES, Epi, PAIR>();
     static_assert(smem <= 232448, "search kernel shared memory");
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         OFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
     }
     static int pf_dist = -1;
     // default: in-order sweep with group 0 prefetching 8 tiles ahead (33 GB instead of 43 GB of DRAM reads at
@@ -771,6 +982,7 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
+#ifdef OFX_DEBUG   // instrumented builds only (allocates + synchronises; see gemm.cu)
     static int prof_on = -1;
     static long long* prof_dev = nullptr;
     if (prof_on < 0) { const char* e = getenv("OFX_TC_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
@@ -779,6 +991,10 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
         OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 256, stream));
         OFX_CUDA(cudaMemcpyToSymbolAsync(g_tc_prof, &prof_dev, sizeof(prof_dev), 0, cudaMemcpyHostToDevice, stream));
     }
+#else
+    constexpr int prof_on = 0;
+    long long* const prof_dev = nullptr;
+#endif
     OFX_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_q, tm_g, sp, ep, kdim / kBK));
     if (prof_on) {
         long long h[8 * 256];
@@ -826,22 +1042,24 @@ int ofx_gallery_pack(const float* gallery, int64_t n_rows, int32_t dim, void* pa
     OFX_TRY(require_sm100());
     const PackedGallery L = gallery_layout(n_rows, dim);
     uint8_t* base = static_cast<uint8_t*>(packed);
+    OFX_CUDA(cudaMemsetAsync(base + L.stats, 0, 256, static_cast<cudaStream_t>(stream)));
     gallery_pack_kernel<<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        gallery, n_rows, dim, reinterpret_cast<__nv_bfloat16*>(base), reinterpret_cast<float*>(base + L.rows_bytes));
+        gallery, n_rows, dim, reinterpret_cast<__nv_bfloat16*>(base), reinterpret_cast<float*>(base + L.rows_bytes),
+        reinterpret_cast<unsigned int*>(base + L.stats));
     OFX_LAUNCH_CHECK();
     return OFX_OK;
 }
 
 size_t ofx_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_query, int32_t k) {
-    if (n_rows < 0 || dim <= 0 || n_query < 0 || k < 1 || k > 48) return 0;
+    if (n_rows < 0 || dim <= 0 || n_query < 0 || k < 1 || k > kMaxK) return 0;
     return search_ws(n_rows, dim, n_query, k).total;
 }
 
 int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows, int32_t dim,
                     int64_t id_offset, const float* queries, int32_t n_query, int32_t k, int32_t metric,
-                    double* out_score, int64_t* out_idx, void* workspace, size_t workspace_bytes,
-                    void* stream) {
-    if (k < 1 || k > 48) return fail(OFX_E_SHAPE, "ofx_topk_search: k %d not in [1,48]", k);
+                    double* out_score, int64_t* out_idx, uint8_t* out_certified, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (k < 1 || k > kMaxK) return fail(OFX_E_SHAPE, "ofx_topk_search: k %d not in [1,%d]", k, kMaxK);
     if (dim <= 0 || dim % 128) return fail(OFX_E_SHAPE, "ofx_topk_search: dim %d must be a multiple of 128", dim);
     if (n_rows < 0 || n_rows >= (1ll << 31) - 256) return fail(OFX_E_SHAPE, "ofx_topk_search: n_rows %lld", (long long)n_rows);
     if (n_query < 0) return fail(OFX_E_SHAPE, "ofx_topk_search: n_query %d", n_query);
@@ -888,7 +1106,7 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
             kWarmRows = e ? atoll(e) : (warm_legacy ? 4096 : 8192);
             if (kWarmRows % 256) kWarmRows = warm_legacy ? 4096 : 8192;
         }
-        const long long warm_rows = W.kcap == 32 ? kWarmRows : 2 * kWarmRows;    // 2 kcap blocks of 128 rows by default
+        const long long warm_rows = kWarmRows * (W.kcap / 32);    // 2 kcap blocks of 128 rows by default
         if (kWarmRows > 0 && n_rows >= 16 * warm_rows) {
             if (warm_legacy) {
                 SearchPlan wp = make_plan(kWarmRows, n_query, sm_count());
@@ -907,18 +1125,24 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
                 if (W.kcap == 32) {
                     EpiBlockMax<64>::Params ep{warm_rows, n_query, thr, 32, prog};
                     OFX_TRY((launch_search_cl<EpiBlockMax<64>, 4, 6>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
-                } else {
+                } else if (W.kcap == 64) {
                     EpiBlockMax<128>::Params ep{warm_rows, n_query, thr, 64, prog};
                     OFX_TRY((launch_search_cl<EpiBlockMax<128>, 3, 5>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
+                } else {
+                    EpiBlockMax<256>::Params ep{warm_rows, n_query, thr, 128, prog};
+                    OFX_TRY((launch_search_cl<EpiBlockMax<256>, 2, 3>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
                 }
             }
         }
         if (W.kcap == 32) {
             EpiTopK<32>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
             OFX_TRY((launch_search_cl<EpiTopK<32>, 4, 6>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
-        } else {
+        } else if (W.kcap == 64) {
             EpiTopK<64>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
             OFX_TRY((launch_search_cl<EpiTopK<64>, 3, 5>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
+        } else {
+            EpiTopK<128>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
+            OFX_TRY((launch_search_cl<EpiTopK<128>, 2, 3>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         }
     }
     MergeArgs ma{};
@@ -930,6 +1154,9 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
     ma.queries = queries; ma.gallery_f32 = gallery_f32; ma.dim = dim; ma.metric = metric; ma.k = k;
     ma.id_offset = id_offset; ma.out_score = out_score; ma.out_idx = reinterpret_cast<long long*>(out_idx);
     ma.thr_enc = n_rows > 0 ? thr : nullptr;
+    ma.max_half_sqnorm = reinterpret_cast<const float*>(pk + L.stats);
+    ma.certified = out_certified;
+#ifdef OFX_DEBUG   // instrumented builds only (allocates + synchronises)
     static int merge_prof = -1;
     static unsigned long long* merge_prof_dev = nullptr;
     if (merge_prof < 0) { const char* e = getenv("OFX_MERGE_PROF"); merge_prof = (e && e[0] == '1') ? 1 : 0; }
@@ -937,12 +1164,15 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
         if (!merge_prof_dev) OFX_CUDA(cudaMalloc(&merge_prof_dev, 64));
         OFX_CUDA(cudaMemsetAsync(merge_prof_dev, 0, 64, st));
     }
+#else
+    constexpr int merge_prof = 0;
+    unsigned long long* const merge_prof_dev = nullptr;
+#endif
     ma.prof = merge_prof ? merge_prof_dev : nullptr;
     const size_t smem = static_cast<size_t>(n_pad + kMergeSmall) * 8;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.need()) {
         OFX_CUDA(cudaFuncSetAttribute(merge_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + kMergeSmall) * 8));
-        configured = true;
     }
     merge_rerank_kernel<<<n_query, kMergeThreads, smem, st>>>(ma);
     OFX_LAUNCH_CHECK();
@@ -953,6 +1183,59 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
         fprintf(stderr, "merge prof (avg cycles per query CTA): gather %llu  sort %llu  re-score %llu ; full sorts %llu of %d ; n_pad %d n_seg %d\n",
                 h[0] / n_query, h[1] / n_query, h[2] / n_query, h[4], n_query, n_pad, W.plan.n_seg);
     }
+    return OFX_OK;
+}
+
+static int exact_chunks(long long n_rows, int k) {
+    long long c = (n_rows + 2047) / 2048;             // at least 2048 rows per chunk
+    const long long cap = 2048 / k < 128 ? 2048 / k : 128;     // topk_merge_kernel takes n_lists * k <= 2048
+    if (c > cap) c = cap;
+    return c < 1 ? 1 : static_cast<int>(c);
+}
+
+size_t ofx_exact_search_workspace_bytes(int64_t n_rows, int32_t n_sel, int32_t k) {
+    if (n_rows < 0 || n_sel < 0 || k < 1 || k > kMaxK) return 0;
+    return align_up(static_cast<size_t>(exact_chunks(n_rows, k)) * n_sel * k * 16, 256) + 256;
+}
+
+int ofx_exact_search(const float* gallery_f32, int64_t n_rows, int32_t dim, int64_t id_offset,
+                     const float* queries, const int32_t* sel, int32_t n_sel, int32_t k, int32_t metric,
+                     double* out_score, int64_t* out_idx, uint8_t* out_certified, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (k < 1 || k > kMaxK) return fail(OFX_E_SHAPE, "ofx_exact_search: k %d not in [1,%d]", k, kMaxK);
+    if (dim <= 0 || dim % 4 || dim > 4096) return fail(OFX_E_SHAPE, "ofx_exact_search: dim %d (multiple of 4, <= 4096)", dim);
+    if (n_rows < 0 || n_sel < 0) return fail(OFX_E_SHAPE, "ofx_exact_search: n_rows %lld, n_sel %d", (long long)n_rows, n_sel);
+    if (metric != OFX_METRIC_DOT && metric != OFX_METRIC_L2) return fail(OFX_E_ARG, "ofx_exact_search: metric %d", metric);
+    if (n_sel == 0) return OFX_OK;
+    if (!queries || !sel || !out_score || !out_idx || (n_rows > 0 && !gallery_f32)) return fail(OFX_E_ARG, "ofx_exact_search: null argument");
+    if (reinterpret_cast<uintptr_t>(gallery_f32) % 16 || reinterpret_cast<uintptr_t>(queries) % 16 || reinterpret_cast<uintptr_t>(workspace) % 256)
+        return fail(OFX_E_ARG, "ofx_exact_search: misaligned pointer");
+    const size_t need = ofx_exact_search_workspace_bytes(n_rows, n_sel, k);
+    if (!workspace || workspace_bytes < need) return fail(OFX_E_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+    OFX_TRY(require_sm100());
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int chunks = exact_chunks(n_rows, k);
+    const size_t n_part = static_cast<size_t>(chunks) * n_sel * k;
+    double* part_s = static_cast<double*>(workspace);
+    long long* part_i = reinterpret_cast<long long*>(part_s + n_part);
+    // padding: idx -1 (0xFF..), score bits 0xFF.. = NaN, never read for idx < 0
+    OFX_CUDA(cudaMemsetAsync(workspace, 0xFF, n_part * 16, st));
+    const long long rows_per_chunk = (n_rows + chunks - 1) / chunks;
+    const size_t smem = sizeof(float) * kExactQ * dim + static_cast<size_t>(kExactWarps) * kExactQ * k * 16;
+    static DeviceOnce configured;
+    if (configured.need())
+        OFX_CUDA(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(sizeof(float) * kExactQ * 4096 + kExactWarps * kExactQ * kMaxK * 16)));
+    if (n_rows > 0) {
+        exact_scan_kernel<<<dim3(chunks, (n_sel + kExactQ - 1) / kExactQ), kExactWarps * 32, smem, st>>>(
+            gallery_f32, n_rows, dim, metric, queries, sel, n_sel, k, rows_per_chunk > 0 ? rows_per_chunk : 1, part_s, part_i);
+        OFX_LAUNCH_CHECK();
+    }
+    topk_merge_kernel<<<n_sel, 128, static_cast<size_t>(chunks) * k * 16, st>>>(
+        part_s, part_i, chunks, n_sel, k, out_score, reinterpret_cast<long long*>(out_idx), sel);
+    OFX_LAUNCH_CHECK();
+    add_offset_kernel<<<(n_sel * k + 255) / 256, 256, 0, st>>>(reinterpret_cast<long long*>(out_idx), sel, n_sel, k, id_offset, out_certified);
+    OFX_LAUNCH_CHECK();
     return OFX_OK;
 }
 

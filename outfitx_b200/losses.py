@@ -39,10 +39,10 @@ class FocalLoss(torch.nn.Module):
 
     def __init__(self, gamma=2, alpha=0.5, reduction="mean"):
         super().__init__()
-        assert gamma >= 0, f"Invalid Value for arg 'gamma': '{gamma}' \n Gamma should be non-negative"
-        assert 0 <= alpha <= 1, f"Invalid Value for arg 'alpha': '{alpha}' \n Alpha should be in range [0, 1]"
-        assert reduction in ["none", "mean", "sum"], (
-            f"Invalid Value for arg 'reduction': '{reduction} \n Supported reduction modes: 'none', 'mean', 'sum'")
+        # same argument checks (and exception type) as the reference constructor, focal_loss.py:9-18
+        assert gamma >= 0, f"gamma must be >= 0, got {gamma}"
+        assert 0 <= alpha <= 1, f"alpha must lie in [0, 1], got {alpha}"
+        assert reduction in ("none", "mean", "sum"), f"reduction must be one of none / mean / sum, got {reduction!r}"
         self.gamma, self.alpha, self.reduction = gamma, alpha, reduction
 
     def forward(self, y_hat: torch.Tensor, y_true: torch.Tensor) -> torch.Tensor:

@@ -9,14 +9,14 @@ B200, so this module splits a host batch into chunks and double-buffers them: ch
 PCIe on a copy stream while chunk i is scored on the compute stream, and results return through
 pinned host buffers.  Everything it calls is the public ``OutfitX`` API; it adds no arithmetic.
 
-``fetch_valid_only=True`` replaces the DMA copies of the padded per-modality tensors by a kernel that
-reads the pinned host tensors in place and fetches only the valid slots (``ofx_fetch_valid_items``,
-44 % fewer bytes at n ~ U{2..16}).  Measured on configs[1] it is SLOWER while the scoring kernels run
-(16.97 vs 14.95 ms per 8192-outfit step): they are persistent and hold every SM's registers / shared
-memory, so the fetch kernel only advances in the gaps, whereas the copy engines need no SM.  It is
-therefore off by default and kept for hosts whose batches are mostly padding.  (A shrinking tail of
-small chunks, meant to shorten the un-overlapped scoring of the last chunk, was measured too: every
-extra chunk costs ~0.8 ms, 16.6 ms per step with chunks 2048 x 3 + 1024 + 512 x 2 -- uniform chunks stay.)
+``score_packed`` takes the batch WITHOUT its zero padding: the valid item rows of all outfits back to back,
+``(sum n_i, dim_per_modality)`` per modality, plus ``lengths (B,)`` -- what a collate produces when it skips the
+``pad_value.expand(...)`` of ``outfit_x_base_processor.py:57-81``.  A chunk of outfits is then ONE contiguous
+row range per modality (one DMA each) and 44 % fewer PCIe bytes at n ~ U{2..16}; on the device the rows are
+addressed through the item-id gather of the device-side collate (slot (b, s) reads row ``off[b] + s``), so the
+arithmetic -- and every output bit -- is that of the padded path.  (Round 1 tried to skip the padding with a kernel
+that read the pinned padded tensors in place; the persistent scoring kernels starve it of SMs, 16.97 vs 14.95 ms.
+The copy engines need no SM, so the fix belongs in the host layout.)
 """
 from __future__ import annotations
 
@@ -34,8 +34,7 @@ class HostScoringPipeline:
     the copies to be asynchronous; pageable tensors work but serialise.
     """
 
-    def __init__(self, model, chunk: int = 2048, fetch_valid_only: bool = False):
-        self.fetch_valid_only = fetch_valid_only
+    def __init__(self, model, chunk: int = 2048):
         if chunk < 1:
             raise ValueError("chunk must be >= 1")
         self.model, self.chunk = model, chunk
@@ -48,6 +47,7 @@ class HostScoringPipeline:
         self._slots = [dict(), dict()]          # device staging buffers, two in flight
         self._free = [torch.cuda.Event(), torch.cuda.Event()]   # slot may be overwritten
         self._ready = [torch.cuda.Event(), torch.cuda.Event()]  # slot's copies have landed
+        self._host = {}                          # pinned scratch for the ids / masks derived from lengths
 
     def _stage(self, slot: int, name: str, src: torch.Tensor) -> torch.Tensor:
         buf = self._slots[slot].get(name)
@@ -58,27 +58,23 @@ class HostScoringPipeline:
         view.copy_(src, non_blocking=True)
         return view
 
-    def _stage_items(self, slot: int, img: torch.Tensor, txt: torch.Tensor, mask_dev: torch.Tensor):
-        """Device copies of one chunk of the per-modality tensors.  Pinned fp32 sources: the valid slots are
-        fetched by a kernel reading host memory in place (padded slots stay stale -- nothing reads them);
-        anything else: plain copies of the whole chunk."""
-        direct = (self.fetch_valid_only and img.is_pinned() and txt.is_pinned() and img.dtype == torch.float32
-                  and txt.dtype == torch.float32 and img.is_contiguous() and txt.is_contiguous() and img.dim() == 3
-                  and img.shape == txt.shape and img.shape[-1] % 4 == 0)
-        if not direct:
-            return self._stage(slot, "img", img), self._stage(slot, "txt", txt)
-        out = []
-        for name in ("img", "txt"):
-            buf = self._slots[slot].get(name)
-            if buf is None or buf.shape[1:] != img.shape[1:] or buf.dtype != img.dtype:
-                buf = torch.zeros((self.chunk,) + tuple(img.shape[1:]), dtype=img.dtype, device=self.dev)
-                self._slots[slot][name] = buf
-            out.append(buf[: img.shape[0]])
-        n, items, dpm = img.shape
-        _lib.check(_lib.lib().ofx_fetch_valid_items(
-            img.data_ptr(), txt.data_ptr(), mask_dev.view(torch.uint8).data_ptr(), n, items, dpm,
-            out[0].data_ptr(), out[1].data_ptr(), torch.cuda.current_stream(self.dev).cuda_stream))
-        return out[0], out[1]
+    def _stage_rows(self, slot: int, name: str, src: torch.Tensor, cap_rows: int) -> torch.Tensor:
+        """Like _stage for a ragged row range: the buffer holds up to cap_rows rows."""
+        buf = self._slots[slot].get(name)
+        if buf is None or buf.shape[1:] != src.shape[1:] or buf.dtype != src.dtype or buf.shape[0] < max(cap_rows, src.shape[0]):
+            buf = torch.empty((max(cap_rows, src.shape[0], 1),) + tuple(src.shape[1:]), dtype=src.dtype, device=self.dev)
+            self._slots[slot][name] = buf
+        view = buf[: src.shape[0]]
+        if src.shape[0]:
+            view.copy_(src, non_blocking=True)
+        return view
+
+    def _pinned(self, name: str, shape, dtype) -> torch.Tensor:
+        t = self._host.get(name)
+        if t is None or t.shape != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype).pin_memory()
+            self._host[name] = t
+        return t
 
     @torch.no_grad()
     def score(self, image_embeddings: torch.Tensor, text_embeddings: torch.Tensor, outfit_mask: torch.Tensor,
@@ -107,7 +103,8 @@ class HostScoringPipeline:
                 if i >= 2:
                     self.copy_stream.wait_event(self._free[s])
                 d = {"mask": self._stage(s, "mask", outfit_mask[lo:hi])}
-                d["img"], d["txt"] = self._stage_items(s, image_embeddings[lo:hi], text_embeddings[lo:hi], d["mask"])
+                d["img"] = self._stage(s, "img", image_embeddings[lo:hi])
+                d["txt"] = self._stage(s, "txt", text_embeddings[lo:hi])
                 if fitb:
                     d["text"] = self._stage(s, "text", target_item_text_embedding[lo:hi])
                     d["cand"] = self._stage(s, "cand", candidate_item_embedding[lo:hi])
@@ -115,6 +112,73 @@ class HostScoringPipeline:
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(self._ready[s])
                 enc = {"image_embeddings": d["img"], "text_embeddings": d["txt"]}
+                probs = self.model.score_cp(outfit_mask=d["mask"], encoder_input_dict=enc)
+                out["probs"][lo:hi].copy_(probs, non_blocking=True)
+                if fitb:
+                    pred, _, _ = self.model.score_fitb(outfit_mask=d["mask"], target_item_text_embedding=d["text"],
+                                                       candidate_item_embedding=d["cand"], encoder_input_dict=enc)
+                    out["pred"][lo:hi].copy_(pred, non_blocking=True)
+                self._free[s].record(self.compute_stream)
+        cur.wait_stream(self.compute_stream)
+        self.compute_stream.synchronize()
+        return out
+
+    @torch.no_grad()
+    def score_packed(self, image_rows: torch.Tensor, text_rows: torch.Tensor, lengths: torch.Tensor,
+                     target_item_text_embedding: Optional[torch.Tensor] = None,
+                     candidate_item_embedding: Optional[torch.Tensor] = None,
+                     out: Optional[Dict[str, torch.Tensor]] = None, max_items: int = 16) -> Dict[str, torch.Tensor]:
+        """As ``score`` for a HOST batch in the packed layout: ``image_rows`` / ``text_rows``
+        ``(sum(lengths), dim_per_modality)`` hold the valid items of outfit 0, then outfit 1, ...;
+        ``lengths (B,)`` integers in ``[0, max_items]`` (a collate truncates to ``max_items`` = 16 first,
+        ``outfit_x_base_processor.py:57-81``).  Bit-identical to ``score`` on the padded tensors."""
+        lens = lengths.detach().to("cpu", torch.int64).flatten()
+        B = lens.numel()
+        if B and (int(lens.min()) < 0 or int(lens.max()) > max_items):
+            raise ValueError(f"lengths must lie in [0, {max_items}]")
+        total = int(lens.sum())
+        if image_rows.shape != text_rows.shape or image_rows.dim() != 2 or image_rows.shape[0] != total:
+            raise ValueError(f"image_rows / text_rows must both be (sum(lengths) = {total}, dim_per_modality)")
+        fitb = candidate_item_embedding is not None
+        if fitb and target_item_text_embedding is None:
+            raise ValueError("FITB scoring needs target_item_text_embedding")
+        if out is None:
+            out = {"probs": torch.empty(B, dtype=torch.float32).pin_memory()}
+            if fitb:
+                out["pred"] = torch.empty(B, dtype=torch.int64).pin_memory()
+        # host side of the collate, vectorised: row offsets, the padding mask and the chunk-local row id of every slot
+        off = torch.zeros(B + 1, dtype=torch.int64)
+        torch.cumsum(lens, 0, out=off[1:])
+        slot = torch.arange(max_items, dtype=torch.int64)
+        mask_h = self._pinned("mask", (B, max_items), torch.bool)
+        torch.ge(slot[None, :], lens[:, None], out=mask_h)
+        ids_h = self._pinned("ids", (B, max_items), torch.int32)
+        chunk_base = off[torch.arange(0, B, self.chunk)].repeat_interleave(self.chunk)[:B]     # first row of each outfit's chunk
+        ids_h.copy_((off[:B, None] - chunk_base[:, None] + slot[None, :]).to(torch.int32))
+        cap_rows = self.chunk * max_items
+        cur = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(cur)
+        self.compute_stream.wait_stream(cur)
+        for i, lo in enumerate(range(0, B, self.chunk)):
+            hi = min(B, lo + self.chunk)
+            r0, r1 = int(off[lo]), int(off[hi])
+            s = i & 1
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(self._free[s])
+                d = {"mask": self._stage(s, "pmask", mask_h[lo:hi]), "ids": self._stage(s, "pids", ids_h[lo:hi]),
+                     "img": self._stage_rows(s, "pimg", image_rows[r0:r1], cap_rows),
+                     "txt": self._stage_rows(s, "ptxt", text_rows[r0:r1], cap_rows)}
+                if fitb:
+                    d["text"] = self._stage(s, "text", target_item_text_embedding[lo:hi])
+                    d["cand"] = self._stage(s, "cand", candidate_item_embedding[lo:hi])
+                self._ready[s].record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(self._ready[s])
+                # the chunk's rows are the "table" of the device-side collate; an empty chunk still needs one row
+                img_t = d["img"] if r1 > r0 else self._slots[s]["pimg"][:1]
+                txt_t = d["txt"] if r1 > r0 else self._slots[s]["ptxt"][:1]
+                enc = {"image_embeddings": img_t, "text_embeddings": txt_t, "item_ids": d["ids"]}
                 probs = self.model.score_cp(outfit_mask=d["mask"], encoder_input_dict=enc)
                 out["probs"][lo:hi].copy_(probs, non_blocking=True)
                 if fitb:
@@ -173,3 +237,11 @@ class HostScoringPipeline:
         cur.wait_stream(self.compute_stream)
         self.compute_stream.synchronize()
         return out
+
+
+def pack_valid_rows(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor, outfit_mask: torch.Tensor):
+    """Padded host batch ``(B, L, dpm)`` x 2 + ``outfit_mask (B, L)`` (True = pad) -> the packed layout of
+    ``HostScoringPipeline.score_packed``: ``(image_rows, text_rows, lengths)``.  Valid slots keep their order.
+    (A convenience for callers that already hold padded tensors; a collate should build the rows directly.)"""
+    keep = ~outfit_mask.bool()
+    return (image_embeddings[keep].contiguous(), text_embeddings[keep].contiguous(), keep.sum(-1).to(torch.int32))

@@ -20,7 +20,7 @@ import torch
 from . import _lib
 
 _METRIC = {"dot": _lib.METRIC_DOT, "l2": _lib.METRIC_L2}
-MAX_K = 48
+MAX_K = 64
 
 
 def shard_rows(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
@@ -79,13 +79,28 @@ def _workspace(nbytes: int, dev) -> torch.Tensor:
     return b
 
 
+class SearchStats:
+    """Counters of the exactness certificate (process-wide, for tests and the bench line)."""
+    queries = 0          # exact-mode queries searched
+    uncertified = 0      # of those, how many the bound could not prove and went to the exhaustive fallback
+
+    @classmethod
+    def reset(cls):
+        cls.queries = cls.uncertified = 0
+
+
 @torch.no_grad()
 def local_search(queries: torch.Tensor, gallery: Gallery, k: int = 10, metric: str = "l2",
-                 exact: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                 exact: bool = True, return_certified: bool = False):
     """Top-k of every query over one shard -> (idx (nq,k) int64 GLOBAL ids, score (nq,k) fp64).
 
-    exact=True re-scores the tensor-core pass's candidates in fp64 from the fp32 rows (bit-exact
-    indices against an fp64 exhaustive search); exact=False returns the bf16-pass ranking."""
+    exact=True re-scores the tensor-core pass's candidates in fp64 from the fp32 rows and PROVES, per query,
+    that nothing the bf16 pass dropped can reach the k-th best exact score (rigorous bf16 error bound, see
+    ``ofx_topk_search``); the few queries it cannot prove (gallery rows closer than bf16 resolves) are
+    re-searched exhaustively in fp64 (``ofx_exact_search``), so the indices ARE those of an fp64 exhaustive
+    search.  Reading the certificate flags costs one small device->host sync per call.
+    exact=False returns the bf16-pass ranking (no certificate, no sync).
+    return_certified=True appends the (nq,) bool tensor "proved by the bound alone"."""
     if metric not in _METRIC:
         raise ValueError(f"metric must be 'dot' or 'l2', got {metric!r}")
     if not 1 <= k <= MAX_K:
@@ -101,17 +116,31 @@ def local_search(queries: torch.Tensor, gallery: Gallery, k: int = 10, metric: s
     L = _lib.lib()
     score = torch.empty(nq, k, dtype=torch.float64, device=dev)
     idx = torch.empty(nq, k, dtype=torch.int64, device=dev)
+    proved = torch.zeros(nq, dtype=torch.bool, device=dev)
     if nq == 0:
-        return idx, score
+        return (idx, score, proved) if return_certified else (idx, score)
+    cert = torch.zeros(nq, dtype=torch.uint8, device=dev) if exact else None
     nbytes = L.ofx_search_workspace_bytes(gallery.n_rows, gallery.dim, nq, k)
     ws = _workspace(nbytes, dev)
     with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(L.ofx_topk_search(
             gallery.packed.data_ptr(), gallery.rows_f32.data_ptr() if exact else None,
             gallery.n_rows, gallery.dim, gallery.id_offset, q.data_ptr(), nq, k, _METRIC[metric],
-            score.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(),
-            torch.cuda.current_stream(dev).cuda_stream))
-    return idx, score
+            score.data_ptr(), idx.data_ptr(), cert.data_ptr() if exact else None, ws.data_ptr(), ws.numel(), st))
+        if exact:
+            proved = cert.bool()
+            sel = torch.nonzero(~proved).flatten().to(torch.int32)       # the one host sync of an exact search
+            SearchStats.queries += nq
+            SearchStats.uncertified += int(sel.numel())
+            if sel.numel():
+                nb = L.ofx_exact_search_workspace_bytes(gallery.n_rows, sel.numel(), k)
+                ws2 = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
+                _lib.check(L.ofx_exact_search(
+                    gallery.rows_f32.data_ptr(), gallery.n_rows, gallery.dim, gallery.id_offset, q.data_ptr(),
+                    sel.data_ptr(), sel.numel(), k, _METRIC[metric], score.data_ptr(), idx.data_ptr(), None,
+                    ws2.data_ptr(), ws2.numel(), st))
+    return (idx, score, proved) if return_certified else (idx, score)
 
 
 @torch.no_grad()

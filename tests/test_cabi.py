@@ -42,6 +42,8 @@ def test_size_queries_without_gpu():
     assert L.ofx_gallery_packed_bytes(1000, 1024) >= 1000 * 1024 * 2 + 4000
     assert L.ofx_search_workspace_bytes(10_000_000, 1024, 8192, 10) > 8192 * 1024 * 2
     assert L.ofx_search_workspace_bytes(1000, 1024, 8, 1000) == 0   # k out of range
+    assert L.ofx_search_workspace_bytes(1000, 1024, 8, 64) > 0      # the reference ranks k = 50
+    assert L.ofx_exact_search_workspace_bytes(10_000_000, 8, 10) >= 128 * 8 * 10 * 16
 
 
 def test_no_cpu_fallback():

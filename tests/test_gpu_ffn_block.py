@@ -1,5 +1,5 @@
 """GPU: the fused feed-forward block (ofx_ffn_block_bf16: LayerNorm -> linear1 -> mish -> linear2
--> +residual in one tcgen05 cta_group::2 kernel) against a torch fp32 evaluation of the same
+-> +residual in one tcgen05 cta_group::2 kernel; OFX_FFN_V1=1 runs the round-1 kernel through the same tests) against a torch fp32 evaluation of the same
 arithmetic (torch TransformerEncoderLayer._ff_block as the reference configures it,
 /root/reference/src/models/outfit_x.py:32-45), with the operands rounded to bf16 where the
 kernel rounds them (LN output, weights, hidden activation)."""
@@ -11,12 +11,21 @@ pytestmark = pytest.mark.gpu
 DM, FP = 512, 2048
 
 
+def _ws(rows, fp):
+    from outfitx_b200 import _lib
+    n = _lib.lib().ofx_ffn_block_workspace_bytes(rows, DM, fp)
+    assert n > 0
+    # poisoned on purpose: the kernel must not depend on what the scratch ring / counters held before
+    return torch.full((n,), 0x5A, dtype=torch.uint8, device="cuda")
+
+
 def _run(x, ln_w, ln_b, w1, b1, w2, b2):
     from outfitx_b200 import _lib
     out = x.clone()
+    ws = _ws(out.shape[0], w1.shape[0])
     _lib.check(_lib.lib().ofx_ffn_block_bf16(
         out.data_ptr(), out.shape[0], DM, w1.shape[0], ln_w.data_ptr(), ln_b.data_ptr(), w1.data_ptr(),
-        b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return out
 
@@ -39,7 +48,7 @@ def _params(seed, fp=FP, d_ffn=2024):
     return ln_w, ln_b, w1.to(torch.bfloat16).contiguous(), b1, w2.to(torch.bfloat16).contiguous(), b2, g
 
 
-@pytest.mark.parametrize("rows", [1, 63, 64, 65, 127, 128, 129, 1000, 128 * 74 + 5, 40000])
+@pytest.mark.parametrize("rows", [1, 63, 64, 65, 127, 128, 129, 255, 256, 257, 1000, 128 * 74 + 5, 256 * 37 * 2 + 130, 40000])
 def test_ffn_block_matches_fp32(rows):
     ln_w, ln_b, w1, b1, w2, b2, g = _params(rows)
     x = torch.randn(rows, DM, device="cuda", generator=g) * 0.7 + 0.05
@@ -60,11 +69,16 @@ def test_ffn_block_rejects_other_shapes():
     from outfitx_b200 import _lib
     x = torch.zeros(4, 1024, device="cuda")
     rc = _lib.lib().ofx_ffn_block_bf16(x.data_ptr(), 4, 1024, 2048, x.data_ptr(), x.data_ptr(), x.data_ptr(),
-                                       x.data_ptr(), x.data_ptr(), x.data_ptr(), None)
+                                       x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 1 << 30, None)
     assert rc == -1
+    assert _lib.lib().ofx_ffn_block_workspace_bytes(4, 1024, 2048) == 0
+    x = torch.zeros(4, 512, device="cuda")
+    rc = _lib.lib().ofx_ffn_block_bf16(x.data_ptr(), 4, 512, 2048, x.data_ptr(), x.data_ptr(), x.data_ptr(),
+                                       x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 256, None)
+    assert rc == -5         # workspace too small
 
 
-@pytest.mark.parametrize("rows", [1, 64, 129, 1000, 128 * 74 + 5, 128 * 74 * 3 + 77])
+@pytest.mark.parametrize("rows", [1, 64, 129, 257, 1000, 128 * 74 + 5, 128 * 74 * 3 + 77])
 def test_ffn_block_emits_next_layer_norm(rows):
     """ofx_ffn_block_ln_bf16: same x as the plain block, and h_next == bf16(LayerNorm(x_new)) with the next
     layer's norm1 terms (rows of several tiles per CTA pair exercise the deferred per-tile hand-over)."""
@@ -76,9 +90,10 @@ def test_ffn_block_emits_next_layer_norm(rows):
     plain = _run(x, ln_w, ln_b, w1, b1, w2, b2)
     out = x.clone()
     h = torch.full((rows + 3, DM), 7.0, device="cuda", dtype=torch.bfloat16)     # 3 guard rows
+    ws = _ws(rows, w1.shape[0])
     _lib.check(_lib.lib().ofx_ffn_block_ln_bf16(
         out.data_ptr(), rows, DM, w1.shape[0], ln_w.data_ptr(), ln_b.data_ptr(), w1.data_ptr(), b1.data_ptr(),
-        w2.data_ptr(), b2.data_ptr(), h.data_ptr(), nw.data_ptr(), nb.data_ptr(),
+        w2.data_ptr(), b2.data_ptr(), h.data_ptr(), nw.data_ptr(), nb.data_ptr(), ws.data_ptr(), ws.numel(),
         torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert torch.equal(out, plain)

@@ -77,3 +77,55 @@ def test_pool_search_rejects_bad_arguments():
         PoolSet.build([torch.zeros(5000, 1024, device="cuda")])
     idx, score = pool_search(q, torch.tensor([0, 0]), ps, k=12)  # pool smaller than k: -1 padding
     assert (idx[:, 10:] == -1).all() and torch.isinf(score[:, 10:]).all()
+
+
+def test_embedding_pickles_flow_into_gallery_and_search(tmp_path):
+    """SURVEY.md N3 end to end: files in the reference's precomputed-embedding wire format
+    (precompute_embedding_script.py:47-53: pickle {'ids': [int], 'embeddings': float32 (N, 2*dpm)}, one file per
+    rank, named {model_name}_embedding_subset_{rank}.pkl) -> load_embedding_pickles -> Gallery.build -> CIR query
+    embedding (text prefix = SECOND half of the target item's row, polyvore_item_dataset.py:75) -> cir_search.
+    The retrieved ITEM IDS must be those of the fp64 oracle run on the same arrays."""
+    import pickle
+    import outfitx_b200 as o
+    from oracle import torch_port
+    from outfitx_b200.search import Gallery, cir_search, load_embedding_pickles
+    n = 9000
+    items = synth.make_items(n, 512, seed=71, dup=40)
+    rng = np.random.Generator(np.random.PCG64(72))
+    item_ids = rng.permutation(np.arange(10_000, 10_000 + 3 * n, 3))[:n].astype(np.int64)      # non-contiguous catalogue ids
+    cuts, paths = (0, 4000, 6500, n), []
+    for r in range(3):
+        d = {"ids": [int(i) for i in item_ids[cuts[r]:cuts[r + 1]]], "embeddings": items[cuts[r]:cuts[r + 1]]}
+        p = tmp_path / f"fashion-clip_embedding_subset_{r}.pkl"
+        with open(p, "wb") as f:
+            pickle.dump(d, f)
+        paths.append(str(p))
+    ids, emb, index = load_embedding_pickles(paths, device="cuda")
+    assert emb.is_cuda and emb.shape == (n, 1024) and torch.equal(ids, torch.from_numpy(item_ids))
+    gallery = Gallery.build(emb)
+    # outfits made of catalogue items, looked up by item id as the datasets do; the target item's text half is the prefix
+    B, dev = 48, "cuda"
+    lengths = synth.make_lengths(B, 73)
+    rows = rng.integers(0, n, size=(B, 16))
+    mask = synth.make_mask(lengths)
+    outfit = emb[torch.from_numpy(rows).to(dev)]
+    outfit[torch.from_numpy(mask).to(dev)] = 0.0
+    targets = rng.integers(0, n, size=B)
+    text = emb[torch.from_numpy(targets).to(dev)][:, 512:].contiguous()
+    sd = synth.make_state_dict(1024, 1024, seed=0)
+    m = o.OutfitX(o.OutfitXConfig(item_encoder=o.ItemEncoderConfig(type="clip")), precision="fp32")
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.to(dev)
+    query = m(o.OutfitComplementaryItemRetrievalTask, outfit_embedding=outfit, outfit_mask=torch.from_numpy(mask).to(dev),
+              target_item_text_embedding=text)
+    # the query embeddings agree with the reference stack ...
+    port = torch_port.ReferencePort.from_numpy(sd)
+    want_q = port.cir(outfit.cpu(), torch.from_numpy(mask), text.cpu()).numpy()
+    assert float(np.abs(query.cpu().numpy() - want_q).max() / np.abs(want_q).max()) <= 1e-3
+    # ... and searching with them returns the oracle's rows, reported as catalogue item ids
+    idx, score = cir_search(query, gallery, k=10, metric="l2")
+    want_i, want_s = R.search(query.cpu().numpy(), items, k=10)
+    assert np.array_equal(idx.cpu().numpy(), want_i)
+    got_ids = ids.to(dev)[idx]
+    assert np.array_equal(got_ids.cpu().numpy(), item_ids[want_i])
+    assert all(index[int(i)] == int(r) for i, r in zip(got_ids[:, 0].cpu(), idx[:, 0].cpu()))

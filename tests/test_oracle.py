@@ -10,7 +10,7 @@ import torch
 
 from oracle import restatement as R
 from oracle import torch_port
-from oracle.make_golden import CASES, case_inputs, digest
+from oracle.make_golden import CASES, case_dims, case_inputs, digest, processor_items
 from outfitx_b200 import synth
 
 
@@ -21,9 +21,9 @@ def _load(golden_dir, name):
 @pytest.mark.parametrize("name,method,d_model,batch", CASES)
 def test_inputs_regenerate_bit_exactly(golden_dir, name, method, d_model, batch):
     g = _load(golden_dir, f"model_{name}.npz")
-    img, txt, emb, mask, text, cand = case_inputs(method, batch)
+    img, txt, emb, mask, text, cand = case_inputs(method, batch, dpm=case_dims(method, d_model)[0])
     assert digest(emb, mask, text, cand) == str(g["input_digest"])
-    sd = synth.make_state_dict(d_model, 1024, seed=0)
+    sd = synth.make_state_dict(d_model, case_dims(method, d_model)[1], seed=0)
     assert digest(*sd.values()) == str(g["weight_digest"])
     assert np.array_equal(mask, g["mask"])
 
@@ -31,8 +31,8 @@ def test_inputs_regenerate_bit_exactly(golden_dir, name, method, d_model, batch)
 @pytest.mark.parametrize("name,method,d_model,batch", CASES)
 def test_restatement_matches_reference(golden_dir, name, method, d_model, batch):
     g = _load(golden_dir, f"model_{name}.npz")
-    sd = synth.make_state_dict(d_model, 1024, seed=0)
-    _, _, emb, mask, text, cand = case_inputs(method, batch)
+    sd = synth.make_state_dict(d_model, case_dims(method, d_model)[1], seed=0)
+    _, _, emb, mask, text, cand = case_inputs(method, batch, dpm=case_dims(method, d_model)[0])
     for dt, tol in ((np.float32, 2e-5), (np.float64, 1e-5)):
         logits = R.cp_forward(sd, emb, mask, dt)
         query = R.cir_forward(sd, emb, mask, text, dt)
@@ -47,8 +47,8 @@ def test_restatement_matches_reference(golden_dir, name, method, d_model, batch)
 @pytest.mark.parametrize("name,method,d_model,batch", CASES)
 def test_torch_port_matches_reference(golden_dir, name, method, d_model, batch):
     g = _load(golden_dir, f"model_{name}.npz")
-    port = torch_port.ReferencePort.from_numpy(synth.make_state_dict(d_model, 1024, seed=0))
-    _, _, emb, mask, text, cand = case_inputs(method, batch)
+    port = torch_port.ReferencePort.from_numpy(synth.make_state_dict(d_model, case_dims(method, d_model)[1], seed=0))
+    _, _, emb, mask, text, cand = case_inputs(method, batch, dpm=case_dims(method, d_model)[0])
     t = torch.from_numpy
     logits = port.cp(t(emb), t(mask)).numpy()
     query = port.cir(t(emb), t(mask), t(text))
@@ -118,3 +118,33 @@ def test_merge_is_shard_invariant():
         i, s = R.merge_topk(np.concatenate([p[0] for p in parts], 1),
                             np.concatenate([p[1] for p in parts], 1), 10)
         assert np.array_equal(i, want_i) and np.array_equal(s, want_s)
+
+
+def test_collate_contract_matches_reference_processors(golden_dir):
+    """tests/golden/processor_clip1024.npz holds what the reference's OWN processors emitted for lists of its
+    task objects (oracle/make_golden.py: write_processor_golden).  The contract the CUDA path is built on
+    (truncate to 16, zero pad rows, mask True on pad, valid items left-aligned, text = second half
+    of the target item's embedding) must regenerate those tensors bit for bit, and the oracle must reproduce the
+    reference model's answers to them."""
+    g = _load(golden_dir, "processor_clip1024.npz")
+    outfits, targets, cands = processor_items(int(g["seed"]))
+    B = len(outfits)
+    emb = np.zeros((B, 16, 1024), np.float32)
+    mask = np.ones((B, 16), bool)
+    for b, o in enumerate(outfits):
+        n = min(len(o), 16)
+        emb[b, :n] = np.stack(o[:n])
+        mask[b, :n] = False
+    for pre in ("cp", "cir"):
+        assert np.array_equal(g[pre + "_outfit_embedding"], emb)
+        assert np.array_equal(g[pre + "_outfit_mask"], mask)
+    assert np.array_equal(g["cir_text"], np.stack(targets)[:, 512:])
+    assert np.array_equal(g["fitb_cand"], np.stack(cands))
+    assert str(g["cp_task"]) == "OutfitCompatibilityPredictionTask"
+    assert str(g["cir_task"]) == str(g["fitb_task"]) == "OutfitComplementaryItemRetrievalTask"   # FITB dispatches as CIR
+    sd = synth.make_state_dict(1024, 1024, seed=int(g["weight_seed"]))
+    np.testing.assert_allclose(R.cp_forward(sd, emb, mask), g["logits"], atol=2e-5)
+    q = R.cir_forward(sd, emb, mask, g["cir_text"])
+    np.testing.assert_allclose(q, g["query"], atol=2e-5)
+    idx, d = R.fitb(g["query"].astype(np.float64), g["fitb_cand"].astype(np.float64))
+    assert np.array_equal(idx, g["fitb_argmin"])

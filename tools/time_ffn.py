@@ -11,14 +11,15 @@ x = torch.randn(rows, DM, device="cuda", generator=g)
 L = _lib.lib()
 st = torch.cuda.current_stream().cuda_stream
 hn = torch.empty(rows, DM, device="cuda", dtype=torch.bfloat16)
+ws = torch.zeros(L.ofx_ffn_block_workspace_bytes(rows, DM, 2048), dtype=torch.uint8, device="cuda")
 def run(t):
     if LN:
         _lib.check(L.ofx_ffn_block_ln_bf16(t.data_ptr(), rows, DM, 2048, ln_w.data_ptr(), ln_b.data_ptr(), w1.data_ptr(),
                                            b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), hn.data_ptr(), ln_w.data_ptr(),
-                                           ln_b.data_ptr(), st))
+                                           ln_b.data_ptr(), ws.data_ptr(), ws.numel(), st))
         return
     _lib.check(L.ofx_ffn_block_bf16(t.data_ptr(), rows, DM, 2048, ln_w.data_ptr(), ln_b.data_ptr(), w1.data_ptr(),
-                                    b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), st))
+                                    b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), ws.data_ptr(), ws.numel(), st))
 y = x.clone(); run(y); torch.cuda.synchronize()
 err = (y - _want(x, ln_w, ln_b, w1, b1, w2, b2)).abs().max().item()
 bufs = [x.clone() for _ in range(4)]
