@@ -352,7 +352,9 @@ def exhaustive_check(queries, gal, result_idx, result_score, k, n_check, dist_ok
         dist.all_gather_into_tensor(gathered, payload)
         gathered = gathered.view((world, 2) + tuple(li.shape))
         li, ls = merge_lists(gathered[:, 0].contiguous(), gathered[:, 1].contiguous().view(torch.float64), k)
-    ok = bool(torch.equal(li, result_idx[s64]) and torch.equal(ls, result_score[s64]))
+    # indices must be identical; the fp64 scores come from two different summation orders (warp-strided re-rank vs
+    # the scan's 16-byte lanes), so they may differ in the last bits
+    ok = bool(torch.equal(li, result_idx[s64]) and torch.allclose(ls, result_score[s64], rtol=1e-12, atol=1e-10))
     return ok, int(sel.numel())
 
 
@@ -417,7 +419,7 @@ def bench_search(ctx, args, n_rows, queries, k_steps, label, peak_kind, embed=No
                      "peak_kind": f"{peak_kind} bf16, {pk['source']}"},
         "gpu_launches": int(launches),
         "verified": ok,
-        "verified_how": f"indices and fp64 scores of {n_chk} queries equal an exhaustive fp64 CUDA-core scan of "
+        "verified_how": f"indices (exactly) and fp64 scores (to 1e-12) of {n_chk} queries equal an exhaustive fp64 CUDA-core scan of "
                         f"every rank's shard (ofx_exact_search), merged across {world} rank(s); outside the timed region",
         "uncertified_frac": unc,
     }

@@ -32,13 +32,14 @@
 // Shared-memory traffic per 256-row tile and CTA: GEMM 1 operands 1.5 MB, GEMM 2 operands 0.75 MB, TMA fills 1.25 MB,
 // staging + H 0.9 MB = 4.4 MB per 32.8k tensor-pipe cycles = 134 B/clk at the MMA floor (the old shape needed 190).
 //
-// Warp roles (16 warps): 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-11 epilogue (two warpgroups
+// Warp roles (16 warps): 0 TMA producer (weights, H), 1 MMA issuer (leader CTA), 2 TMEM allocator + peer loader,
+// 3 exporter, 4-11 epilogue (two warpgroups
 // alternating hidden chunks, then the residual epilogue), 12-15 LayerNorm (prologue LN2 -> H; norm1 of the next layer
-// for the previous tile in their idle time).  Registers re-partitioned with setmaxnreg (80 / 128 / 176: they sum to the 512 x 128 the CTA is launched with -- the pool is the CTA's own allocation).
+// for the previous tile in their idle time).  Registers re-partitioned with setmaxnreg (80 / 152 / 128: they sum to the 512 x 128 the CTA is launched with -- the pool is the CTA's own allocation).
 //
 // Cross-cluster protocol (global int counters, zeroed per launch):
-//   uflag[group][side][rank][slot] += 1 per epilogue warp once its rows of a chunk are in that scratch slot (a slot's
-//                                     tenants follow one another, so 4 x generation identifies the chunk)
+//   uflag[group][side][rank][slot] += 1 per epilogue warp once its part of a chunk is in that scratch slot (a slot's
+//                                     tenants follow one another, so 8 x generation identifies the chunk)
 //   uack [group][side]             += 1 per k-block of side's chunks the partner has pulled into its shared memory
 //   xflag[group][rank][side]       += 1 per epilogue warp and tile once its new x columns are in global memory
 // Every wait is on a counter of STRICTLY earlier chunks, so the two pairs cannot deadlock as long as
@@ -71,8 +72,8 @@ constexpr int SMEM_BYTES = 1024 + H_BYTES + STG_BYTES + NS * SLOT_BYTES + BAR_BY
 constexpr int NTHREADS = 512;
 constexpr int EPI_WARP0 = 4, LN_WARP0 = 12;
 constexpr uint32_t TM_OUT = 0, TM_ACC1 = 256;   // TMEM columns
-constexpr int NSLOT = 4;              // scratch slots per (group, side, rank)
-constexpr int LAG = 1;                // the partner's chunk j is consumed in step j + LAG
+constexpr int NSLOT = 16;             // scratch slots per (group, side, rank): two tiles of chunks (nch <= 8), see slot_of()
+constexpr int LAG = 2;                // the partner's chunk j is consumed in step j + LAG (its announcement is deferred by one chunk of the producing warpgroup)
 
 struct Params {
     float* x;               // (rows, 512) fp32 residual stream, updated in place
@@ -89,6 +90,10 @@ struct Params {
     int* uflag;             // [n_groups][side 2][rank 2][NSLOT]
     int* uack;              // [n_groups][side 2]
     int* xflag;             // [n_groups][rank 2][side 2]
+    __nv_bfloat16* scratch; // [n_groups][side 2][rank 2][NSLOT][128][128] bf16: the hidden-chunk exchange ring
+    __nv_bfloat16* hbuf;    // [n_ctas][2][128][512] bf16: LN2 rows staged one tile ahead by the LayerNorm warps
+    long long* prof;        // instrumented builds (OFX_FFN_PROF=1): 32 cycle counters per CTA, else nullptr
+    int mode;               // instrumented builds (OFX_FFN2_MODE): bit 0 = the weight producer pulls the partner's chunks itself
 };
 
 __device__ __forceinline__ float mish_fast(float x) {
@@ -139,10 +144,21 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity, const c
 __device__ __forceinline__ void flag_wait(const int* ptr, int target, const char*, int = 0, int = 0) { wait_flag_ge(ptr, target); }
 #endif
 
+#ifdef OFX_DEBUG
+#define PROF(slot, stmt) do { if (p.prof) { const long long tq__ = clock64(); stmt; prof_acc[slot] += clock64() - tq__; } else { stmt; } } while (0)
+#define PROF_DECL() long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64()
+#define PROF_DUMP(base) do { if (p.prof && lane == 0) { long long* o__ = p.prof + blockIdx.x * 32 + (base); o__[0] = clock64() - prof_t0; \
+        for (int i__ = 0; i__ < 7; ++i__) o__[1 + i__] = prof_acc[i__]; } } while (0)
+#else
+#define PROF(slot, stmt) do { stmt; } while (0)
+#define PROF_DECL() do { } while (0)
+#define PROF_DUMP(base) do { } while (0)
+#endif
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
                   const __grid_constant__ CUtensorMap tm_ust, const __grid_constant__ CUtensorMap tm_uld,
-                  const Params p) {
+                  const __grid_constant__ CUtensorMap tm_h, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -158,7 +174,11 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
     uint64_t* out_empty = out_full + 1;         //       leader's: 16 arrivals
     uint64_t* h_full = out_empty + 1;           //       leader's: 16 LN-warp arrivals
     uint64_t* h_empty = h_full + 1;             //       per CTA (multicast commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + 1);
+    uint64_t* h_staged = h_empty + 1;           //       per CTA: 4 LN-warp arrivals, the next tile's LN2 rows are in hbuf
+    uint64_t* hbuf_free = h_staged + 1;         // [2]   per CTA: producer arrival, that half of hbuf has been pulled into H and consumed
+    uint64_t* stg_full = hbuf_free + 2;         // [8]   per CTA: epilogue warp w has staged its part of a hidden chunk
+    uint64_t* stg_free = stg_full + N_EPI_WARPS; // [8]  per CTA: the exporter's bulk store has read warp w's staging block
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + N_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -176,12 +196,20 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
     // scratch rows: ((((group * 2 + side) * 2 + rank) * NSLOT + slot) * 128 + row), 128 hidden columns each
     const int my_srow = ((group * 2 + side) * 2 + static_cast<int>(rank)) * NSLOT * ROWS;
     const int peer_srow = ((group * 2 + (side ^ 1)) * 2 + static_cast<int>(rank)) * NSLOT * ROWS;
+    // Chunk seq (running number over this group's tiles) lives in scratch slot (tile parity, j) and is that slot's
+    // gen-th tenant.  Two tiles of slots make acknowledgements unnecessary: a pair cannot finish tile t - 1 without ALL of
+    // the partner's chunks of tile t - 1, which the partner produces only after its MMA warp has issued every peer GEMM 2
+    // of tile t - 2 -- i.e. after the bulk loads that emptied the slots of tile t - 2 have completed.  (An
+    // acknowledgement counter was tried first: the release in front of each atomic cost the MMA warp ~20 % of its time.)
+    auto slot_of = [&](int seq) { return ((seq / nch) & 1) * nch + seq % nch; };
+    auto gen_of = [&](int seq) { return (seq / nch) >> 1; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_w1);
         tma_prefetch_desc(&tm_w2);
         tma_prefetch_desc(&tm_ust);
         tma_prefetch_desc(&tm_uld);
+        tma_prefetch_desc(&tm_h);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NS; ++i) {
@@ -190,12 +218,19 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc1_full[i], 1);
-            mbar_init(&u_full[i], N_EPI_WARPS);            // 4 warps of a warpgroup x 2 CTAs
+            mbar_init(&u_full[i], 2 * N_EPI_WARPS);        // all 8 epilogue warps x 2 CTAs
         }
         mbar_init(out_full, 1);
         mbar_init(out_empty, 2 * N_EPI_WARPS);
-        mbar_init(h_full, 2 * N_LN_WARPS);
+        mbar_init(h_full, 1);                   // leader's arrive.expect_tx; the bytes of both CTAs' bulk loads
         mbar_init(h_empty, 1);
+        mbar_init(h_staged, N_LN_WARPS);
+        mbar_init(&hbuf_free[0], 1);
+        mbar_init(&hbuf_free[1], 1);
+        for (int i = 0; i < N_EPI_WARPS; ++i) {
+            mbar_init(&stg_full[i], 1);
+            mbar_init(&stg_free[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
@@ -210,11 +245,12 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (weights + the partner's hidden chunks)
         if (lane == 0) {
+            PROF_DECL();
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t full_addr0 = mapa_shared(smem_u32(&w_full[0]), 0);
             auto acquire = [&]() -> uint32_t {      // waits for the slot, arms the leader's barrier, returns its cluster address
-                bar_wait(&w_empty[stage], phase ^ 1, "w_empty", stage);
+                PROF(0, bar_wait(&w_empty[stage], phase ^ 1, "w_empty", stage));
                 if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * SLOT_BYTES);   // both CTAs' bytes
                 return full_addr0 + stage * 8;
             };
@@ -236,18 +272,35 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
             auto g2own = [&](int j) {
                 for (int i = 0; i < 2; ++i) w2slot((side * nch + j) * CH + i * 64);
             };
-            auto g2peer = [&](int j, int seq) {      // seq = running chunk number of the partner's chunk j
-                flag_wait(peer_uflag + seq % NSLOT, 4 * (seq / NSLOT + 1), "peer_uflag", seq);   // all four warps of the partner CTA have stored chunk seq
-                fence_proxy_async_all();                        // acquired generic-proxy view -> the bulk loads below
+            auto g2peer = [&](int j, int seq) {      // the A slots (the partner's chunk) belong to the peer loader (warp 2)
+                if (p.mode & 1) {
+                    flag_wait(peer_uflag + slot_of(seq), N_EPI_WARPS * (gen_of(seq) + 1), "peer_uflag", seq);
+                    fence_proxy_async_all();
+                }
                 for (int i = 0; i < 2; ++i) {
-                    const uint32_t bar = acquire();
-                    tma_load_2d_pair(s_w + stage * SLOT_BYTES, &tm_uld, bar, i * 64, peer_srow + (seq % NSLOT) * ROWS, kEvictFirst);
+                    if (p.mode & 1) {
+                        const uint32_t bar = acquire();
+                        tma_load_2d_pair(s_w + stage * SLOT_BYTES, &tm_uld, bar, i * 64, peer_srow + slot_of(seq) * ROWS, kEvictFirst);
+                    }
                     advance();
                     w2slot(((side ^ 1) * nch + j) * CH + i * 64);
                 }
             };
             int seq0 = 0;       // chunk number of this tile's chunk 0
+            uint32_t hph = 0;
+            const uint32_t hfull_addr = mapa_shared(smem_u32(h_full), 0);
+            const int hrow0 = static_cast<int>(blockIdx.x) * 2 * ROWS;
             for (int t = group; t < n_tiles; t += n_groups, seq0 += nch) {
+                // this tile's LN2 rows: staged in hbuf by the LayerNorm warps during the previous tile; H itself is free
+                // once GEMM 1 of the previous tile has retired
+                PROF(2, bar_wait(h_staged, hph, "h_staged", t));
+                PROF(2, bar_wait(h_empty, hph ^ 1, "h_empty", t));
+                if (t != group) mbar_arrive(&hbuf_free[hph ^ 1]);     // the previous tile's half of hbuf may be refilled
+                if (rank == 0) mbar_arrive_expect_tx(h_full, 2 * H_BYTES);
+#pragma unroll 1
+                for (int kb = 0; kb < KB1; ++kb)
+                    tma_load_2d_pair(s_h + kb * KBLK_BYTES, &tm_h, hfull_addr, kb * 64, hrow0 + static_cast<int>(hph) * ROWS, kEvictFirst);
+                hph ^= 1;
                 g1(0);
                 if (nch > 1) g1(1);
                 for (int j = 0; j < nch; ++j) {
@@ -257,6 +310,7 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
                 }
                 for (int j = nch > LAG ? nch - LAG : 0; j < nch; ++j) g2peer(j, seq0 + j);
             }
+            PROF_DUMP(0);
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader only)
@@ -269,11 +323,20 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
             const uint32_t h_lo = ((smem_u32(s_h) & 0x3FFFF) >> 4) | (1u << 16);
             const uint32_t w_lo = ((smem_u32(s_w) & 0x3FFFF) >> 4) | (1u << 16);
             auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+            PROF_DECL();
             int stage = 0;
             uint32_t phase = 0, tphase = 0, uph = 0;
+            uint32_t ready = 0;     // result of the early poll of w_full[stage]
+            // waits for ring slot `stage`, then polls the NEXT slot's barrier: a try_wait costs ~100 cycles even on a
+            // completed phase, and the MMAs of a slot run for only 512, so the poll is issued before them and its
+            // latency overlaps their issue instead of opening a bubble in the tensor pipe (the round-1 kernel's trick)
             auto wait_slot = [&]() -> uint32_t {     // this ring slot's descriptor base
-                bar_wait(&w_full[stage], phase, "w_full", stage);
+                if (!ready) PROF(0, bar_wait(&w_full[stage], phase, "w_full", stage));
                 tc_fence_after();
+                int ns = stage + 1;
+                uint32_t nph = phase;
+                if (ns == NS) { ns = 0; nph ^= 1; }
+                ready = mbar_test_wait(&w_full[ns], nph) ? 1u : 0u;      // a probe, not a wait: it must not hold back this slot's MMAs
                 return w_lo + stage * (SLOT_BYTES >> 4);
             };
             auto release_slot = [&]() {              // inside the elected lane: frees the slot in both CTAs when the MMAs retire
@@ -305,7 +368,7 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
                 __syncwarp();
             };
             auto g2own = [&](int j, bool first) {      // A = bf16 hidden chunk in TMEM (written over acc1[j&1] by the epilogue)
-                bar_wait(&u_full[j & 1], (uph >> (j & 1)) & 1, "u_full", j);
+                PROF(1, bar_wait(&u_full[j & 1], (uph >> (j & 1)) & 1, "u_full", j));
                 uph ^= 1u << (j & 1);
                 tc_fence_after();
                 const uint32_t a_t = tmem_base + TM_ACC1 + (j & 1) * CH;
@@ -326,7 +389,6 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
                 for (int i = 0; i < 2; ++i) {
                     const uint32_t a = wait_slot();
                     const int a_stage = stage;
-                    if (lane == 0) red_release_gpu_add(peer_uack, 1);   // the scratch slot's k-block has left global memory
                     advance();
                     const uint32_t b = wait_slot();
                     if (elect_one()) {
@@ -341,13 +403,13 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
                 }
             };
             for (int t = group; t < n_tiles; t += n_groups) {
-                bar_wait(h_full, tphase, "h_full", t);
+                PROF(2, bar_wait(h_full, tphase, "h_full", t));
                 tc_fence_after();
                 g1(0, nch == 1);
                 if (nch > 1) g1(1, nch == 2);
                 for (int j = 0; j < nch; ++j) {
                     if (j == 0) {   // the previous tile's output has left TMEM
-                        bar_wait(out_empty, tphase ^ 1, "out_empty", t);
+                        PROF(3, bar_wait(out_empty, tphase ^ 1, "out_empty", t));
                         tc_fence_after();
                     }
                     g2own(j, j == 0);
@@ -359,149 +421,238 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
                 __syncwarp();
                 tphase ^= 1;
             }
+            PROF_DUMP(8);
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ peer loader (one thread): pulls the partner's hidden
+        // chunks into the ring.  It walks the same slot schedule as the weight producer and owns the A slots of the peer
+        // GEMM 2; waiting for the partner's counter and the proxy fence behind it (acquired generic view -> bulk load)
+        // cost ~2.5k cycles per chunk, during which the weight producer -- which used to do this -- fed nothing.
+        if (lane == 0 && !(p.mode & 1)) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t full_addr0 = mapa_shared(smem_u32(&w_full[0]), 0);
+            // Slots owned by the weight producer are WAITED for as well (not just counted): an mbarrier wait only tells
+            // "the phase of this parity has completed", so a waiter must never be more than one revolution away from the
+            // ring's real position -- counting ahead made the first wait of this thread pass on the fresh barriers.
+            auto skip = [&](int n) {
+                for (int i = 0; i < n; ++i) {
+                    bar_wait(&w_empty[stage], phase ^ 1, "w_empty(s)", stage);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+            };
+            auto g2peer = [&](int seq) {
+                flag_wait(peer_uflag + slot_of(seq), N_EPI_WARPS * (gen_of(seq) + 1), "peer_uflag", seq);   // the partner CTA has stored chunk seq
+                fence_proxy_async_all();
+                for (int i = 0; i < 2; ++i) {
+                    bar_wait(&w_empty[stage], phase ^ 1, "w_empty(p)", stage);
+                    if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 2 * SLOT_BYTES);
+                    tma_load_2d_pair(s_w + stage * SLOT_BYTES, &tm_uld, full_addr0 + stage * 8, i * 64, peer_srow + slot_of(seq) * ROWS, kEvictFirst);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                    skip(1);      // the W2 slot behind it
+                }
+            };
+            int seq0 = 0;
+            for (int t = group; t < n_tiles; t += n_groups, seq0 += nch) {
+                skip(nch > 1 ? 8 : 4);                       // G1(0), G1(1)
+                for (int j = 0; j < nch; ++j) {
+                    skip(2);                                 // G2own(j)
+                    if (j + 2 < nch) skip(4);                // G1(j + 2)
+                    if (j >= LAG) g2peer(seq0 + j - LAG);
+                }
+                for (int j = nch > LAG ? nch - LAG : 0; j < nch; ++j) g2peer(seq0 + j);
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------ exporter (one warp): hands the staged hidden chunks to
+        // the partner.  Plain coalesced copies, staging block -> L2 scratch (4 rows of 128 B per instruction), then ONE
+        // release on the chunk's counter.  A TMA bulk store was tried first: its completion wait and the proxy fence that
+        // must precede the generic-proxy release cost ~3k cycles per chunk (ncu: FENCE.VIEW.ASYNC + ERRBAR + MEMBAR = 9 %
+        // of all stall samples), first on the epilogue warps -- i.e. on the G1 -> E -> G2 chain -- then on a dedicated
+        // thread that could not keep up with one chunk per 4k cycles.  Generic stores need neither.
+        {
+            uint32_t ph = 0;
+            int seq = 0;
+            const int r4 = lane >> 3, c16 = lane & 7;
+            for (int t = group; t < n_tiles; t += n_groups) {
+                for (int j = 0; j < nch; ++j, ++seq) {
+                    uint8_t* slot = reinterpret_cast<uint8_t*>(p.scratch) + (static_cast<size_t>(my_srow) + slot_of(seq) * ROWS) * (CH * 2);
+#pragma unroll 1
+                    for (int w = 0; w < N_EPI_WARPS; ++w) {
+                        bar_wait(&stg_full[w], ph, "stg_full", seq, w);
+                        const uint32_t blk = smem_u32(s_stg + w * STG_WARP_BYTES);
+                        uint4 v[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + r4;
+                            v[it] = lds128(blk + r * 128 + ((c16 ^ (r & 7)) << 4));
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&stg_free[w]);          // the block may be rewritten
+                        uint8_t* dst = slot + static_cast<size_t>((w & 3) * 32 + r4) * (CH * 2) + (w >> 2) * 128 + c16 * 16;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it)
+                            asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + static_cast<size_t>(it) * 4 * (CH * 2)),
+                                         "r"(v[it].x), "r"(v[it].y), "r"(v[it].z), "r"(v[it].w) : "memory");
+                    }
+                    ph ^= 1;
+                    __syncwarp();        // every lane's stores happen-before lane 0's release (cumulative at gpu scope)
+                    if (lane == 0) red_release_gpu_add(my_uflag + slot_of(seq), N_EPI_WARPS);
+                }
+            }
         }
     }
     } else if (warp < LN_WARP0) {
-        // ------------------------------------------------------------ epilogue warps (everything in slabs of 16 columns:
-        // 128 registers without spills, the LayerNorm warpgroup gets the rest)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;" ::: "memory");
+        // ------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                       // TMEM lane quarter = rows q*32 .. +31 of this CTA's 128
-        const int wg = (warp - EPI_WARP0) >> 2;       // warpgroup: hidden chunks j = wg (mod 2); output column half in the drain
+        const int wg = (warp - EPI_WARP0) >> 2;       // warpgroup: which 64 of a chunk's 128 hidden units; output column half in the drain
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         uint8_t* stg = s_stg + (warp - EPI_WARP0) * STG_WARP_BYTES;      // this warp's 32-row x 128-byte staging block
         const uint32_t stg_u = smem_u32(stg);
         const uint32_t stg_row = stg_u + lane * 128;
         const int sw = lane & 7;
-        const uint32_t ufull = mapa_shared(smem_u32(&u_full[wg]), 0);
+        const uint32_t ufull0 = mapa_shared(smem_u32(&u_full[0]), 0);
+        const uint32_t ufull1 = mapa_shared(smem_u32(&u_full[1]), 0);
         const uint32_t oempty = mapa_shared(smem_u32(out_empty), 0);
         uint32_t a1ph = 0, tphase = 0;
         int seq0 = 0;
-        // E(j): bf16(mish(acc1 + b1)) of this warp's 32 rows x 128 hidden units -> TMEM (own GEMM 2) and scratch (partner)
+        const int ew = warp - EPI_WARP0;
+        uint32_t fph = 0;
+        bool pending_free = false;     // a staged block has been handed to the exporter and not yet waited for
+        PROF_DECL();
+        auto staging_free = [&]() {    // before any write to this warp's staging block
+            if (pending_free) {
+                PROF(1, bar_wait(&stg_free[ew], fph, "stg_free", ew));
+                fph ^= 1;
+                pending_free = false;
+            }
+        };
+        // E(j): bf16(mish(acc1 + b1)) of this warp's 32 rows x 64 hidden units -> TMEM (own GEMM 2) and scratch (partner).
+        // ALL eight warps work on every chunk (two per lane quarter, 64 columns each): what limits the block is the
+        // LATENCY G1(j) -> E(j) -> G2(j) -- the MMA warp can run only one GEMM 1 ahead (two accumulators) -- so a chunk
+        // must not sit in one warpgroup for 8k cycles.  The bf16 chunk overwrites its own fp32 accumulator: the warp of
+        // the upper 64 columns stores into columns the lower warp reads, hence both load their columns completely and
+        // meet at a named barrier before the first store.  The 64 bias values sit two per lane, broadcast by shuffles.
         auto mish_chunk = [&](int j, int seq) {
-            const float4* bias4 = reinterpret_cast<const float4*>(p.b1 + (side * nch + j) * CH);
-            float4 bv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) bv[i] = __ldg(bias4 + i);
-            bar_wait(&acc1_full[wg], a1ph, "acc1_full", j, seq);
-            a1ph ^= 1;
+            const int b = j & 1;
+            const float2 bl = __ldg(reinterpret_cast<const float2*>(p.b1 + (side * nch + j) * CH + wg * 64) + lane);
+            PROF(0, bar_wait(&acc1_full[b], (a1ph >> b) & 1, "acc1_full", j, seq));
+            a1ph ^= 1u << b;
             tc_fence_after();
-            const uint32_t t_acc = t_lane + TM_ACC1 + wg * CH;
-#pragma unroll 1
-            for (int sl = 0; sl < 8; ++sl) {
-                uint32_t raw[16];
-                tmem_ld_32x16(t_acc + sl * 16, raw);
-                tmem_ld_wait();
+            const uint32_t t_acc = t_lane + TM_ACC1 + b * CH;
+            uint32_t raw[64];
+            {
+                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[0]);
+                uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&raw[32]);
+                tmem_ld_32x32(t_acc + wg * 64, lo);
+                tmem_ld_32x32(t_acc + wg * 64 + 32, hi);
+            }
+            tmem_ld_wait();
+            tc_fence_before();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");      // the quarter's two warps have read their columns
+            tc_fence_after();
+            staging_free();      // the previous chunk's bulk store has read the staging block
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
                 uint32_t w[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 bb = bv[i];
-                    const float v0 = mish_fast(__uint_as_float(raw[4 * i + 0]) + bb.x);
-                    const float v1 = mish_fast(__uint_as_float(raw[4 * i + 1]) + bb.y);
-                    const float v2 = mish_fast(__uint_as_float(raw[4 * i + 2]) + bb.z);
-                    const float v3 = mish_fast(__uint_as_float(raw[4 * i + 3]) + bb.w);
+                    const int src = sl * 8 + i * 2;        // lanes holding bias[16 sl + 4 i .. +3] (two values each)
+                    const float bx = __shfl_sync(0xffffffffu, bl.x, src), by = __shfl_sync(0xffffffffu, bl.y, src);
+                    const float bz = __shfl_sync(0xffffffffu, bl.x, src + 1), bw = __shfl_sync(0xffffffffu, bl.y, src + 1);
+                    const float v0 = mish_fast(__uint_as_float(raw[16 * sl + 4 * i + 0]) + bx);
+                    const float v1 = mish_fast(__uint_as_float(raw[16 * sl + 4 * i + 1]) + by);
+                    const float v2 = mish_fast(__uint_as_float(raw[16 * sl + 4 * i + 2]) + bz);
+                    const float v3 = mish_fast(__uint_as_float(raw[16 * sl + 4 * i + 3]) + bw);
                     w[2 * i] = pack_bf16(v0, v1);
                     w[2 * i + 1] = pack_bf16(v2, v3);
                 }
-                if (sl < 7) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) bv[i] = __ldg(bias4 + (sl + 1) * 4 + i);
-                }
-                // in place: columns [8 sl, 8 sl + 8) of the accumulator, which this thread has already read past
-                tmem_st_32x8(t_acc + sl * 8, w);
-                if (sl == 4) {       // the staging block still holds k-block 0: its bulk store must have read it
-                    if (lane == 0) tma_store_wait_read();
-                    __syncwarp();
-                }
-                sts128(stg_row + ((((sl & 3) * 2 + 0) ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
-                sts128(stg_row + ((((sl & 3) * 2 + 1) ^ sw) << 4), make_uint4(w[4], w[5], w[6], w[7]));
-                if ((sl & 3) == 3) {        // a 64-unit k-block of this warp's rows is staged: hand it to the partner
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (sl == 3 && seq >= NSLOT) flag_wait(my_uack, 2 * (seq - NSLOT + 1), "uack", seq);   // the slot's previous tenant has been pulled
-                        tma_store_2d(&tm_ust, stg, (sl >> 2) * 64, my_srow + (seq % NSLOT) * ROWS + q * 32);
-                        tma_store_commit();
-                    }
-                }
+                tmem_st_32x8(t_acc + wg * 32 + sl * 8, w);
+                sts128(stg_row + (((sl * 2 + 0) ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+                sts128(stg_row + (((sl * 2 + 1) ^ sw) << 4), make_uint4(w[4], w[5], w[6], w[7]));
             }
+            // this warp's 32 rows x 64 units (one k-block of the chunk) are staged: the exporter hands them to the partner
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stg_full[ew]);
+            pending_free = true;
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_cluster(ufull);           // own GEMM 2 of this chunk may start
-                tma_store_wait_all();                  // the partner's copy is in global memory
-                fence_proxy_async_all();
-                __threadfence();
-                red_release_gpu_add(my_uflag + seq % NSLOT, 1);
-            }
-            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(b ? ufull1 : ufull0);           // own GEMM 2 of this chunk may start
         };
         for (int t = group; t < n_tiles; t += n_groups, seq0 += nch) {
 #pragma unroll 1
-            for (int j = wg; j < nch; j += 2) mish_chunk(j, seq0 + j);
-            // ---- residual epilogue: x[:, side*256 + ...] <- x + out + b2 for this warp's 32 rows x 128 columns, 8 slabs
-            // of 16 columns: TMEM -> registers (thread = row) -> staging block (64-byte rows, chunk rotation keeps both
-            // phases bank-conflict free) -> lane = (row % 8, 16-byte chunk): every global access of the warp is 8 row
-            // segments of 64 B.  Residual rows are prefetched one slab ahead.
+            for (int j = 0; j < nch; ++j) PROF(4, mish_chunk(j, seq0 + j));
+            staging_free();
+            // ---- residual epilogue: x[:, side*256 + ...] <- x + out + b2 for this warp's 32 rows x 128 columns, 4 slabs
+            // of 32 columns: TMEM -> registers (thread = row) -> swizzled staging block -> lane = (row % 4, 16-byte chunk):
+            // every global access of the warp is 4 full 128-byte row segments.  The residual rows of slab s+1 are requested
+            // before slab s is touched (two register buffers), so their L2 latency hides behind a whole slab.
             const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + q * 32;
             const int col0 = side * NOUT + wg * 128;
-            const int sub_row = lane >> 2, chunk = lane & 3;
-            const int rows_valid = n_rows - static_cast<int>(row0) - sub_row;   // row 8i+sub_row live iff 8i < rows_valid
-            float4 res[4], b4;
+            const int sub_row = lane >> 3, chunk = lane & 7;
+            const int rows_valid = n_rows - static_cast<int>(row0) - sub_row;   // row 4i+sub_row live iff 4i < rows_valid
+            float4 res[2][8], b4[2];
             auto load_res = [&](int sl) {
-                const float* xp = p.x + (row0 + sub_row) * DM + col0 + sl * 16 + chunk * 4;
-                b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + sl * 16 + chunk * 4));
+                const float* xp = p.x + (row0 + sub_row) * DM + col0 + sl * 32 + chunk * 4;
+                b4[sl & 1] = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + sl * 32 + chunk * 4));
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    res[i] = 8 * i < rows_valid ? ldg128(xp + static_cast<long long>(8 * i) * DM) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 8; ++i)
+                    res[sl & 1][i] = 4 * i < rows_valid ? ldg128(xp + static_cast<long long>(4 * i) * DM) : make_float4(0.f, 0.f, 0.f, 0.f);
             };
             load_res(0);
-            bar_wait(out_full, tphase, "out_full", t);
+            PROF(5, bar_wait(out_full, tphase, "out_full", t));
             tphase ^= 1;
             tc_fence_after();
-#pragma unroll 1
-            for (int sl = 0; sl < 8; ++sl) {
-                float* xp = p.x + (row0 + sub_row) * DM + col0 + sl * 16 + chunk * 4;
-                uint32_t raw[16];
-                tmem_ld_32x16(t_lane + TM_OUT + wg * 128 + sl * 16, raw);
+#ifdef OFX_DEBUG
+            const long long drain_t0 = clock64();
+#endif
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+                if (sl < 3) load_res(sl + 1);
+                float* xp = p.x + (row0 + sub_row) * DM + col0 + sl * 32 + chunk * 4;
+                uint32_t raw[32];
+                tmem_ld_32x32(t_lane + TM_OUT + wg * 128 + sl * 32, raw);
                 tmem_ld_wait();
                 __syncwarp();        // the previous slab's phase B has finished reading the staging block
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    sts128(stg_u + lane * 64 + (((i + (lane >> 1)) & 3) << 4), make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]));
+                for (int i = 0; i < 8; ++i)
+                    sts128(stg_row + ((i ^ sw) << 4), make_uint4(raw[4 * i], raw[4 * i + 1], raw[4 * i + 2], raw[4 * i + 3]));
                 __syncwarp();
-                float4 v[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = 8 * i + sub_row;
-                    const uint4 u = lds128(stg_u + r * 64 + (((chunk + (r >> 1)) & 3) << 4));
-                    v[i].x = __uint_as_float(u.x) + b4.x + res[i].x; v[i].y = __uint_as_float(u.y) + b4.y + res[i].y;
-                    v[i].z = __uint_as_float(u.z) + b4.z + res[i].z; v[i].w = __uint_as_float(u.w) + b4.w + res[i].w;
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + sub_row;
+                    const uint4 u = lds128(stg_u + r * 128 + ((chunk ^ (r & 7)) << 4));
+                    float4 v = res[sl & 1][i];
+                    const float4 bb = b4[sl & 1];
+                    v.x += __uint_as_float(u.x) + bb.x; v.y += __uint_as_float(u.y) + bb.y;
+                    v.z += __uint_as_float(u.z) + bb.z; v.w += __uint_as_float(u.w) + bb.w;
+                    if (4 * i < rows_valid) stg128(xp + static_cast<long long>(4 * i) * DM, v);
                 }
-                if (sl < 7) load_res(sl + 1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (8 * i < rows_valid) stg128(xp + static_cast<long long>(8 * i) * DM, v[i]);
             }
             tc_fence_before();
-            if (p.h_next) __threadfence();      // the new columns must be visible to the partner pair's LayerNorm warps too
-            __syncwarp();
+            __syncwarp();        // the lanes' x stores happen-before lane 0's release below (cumulative at gpu scope)
             if (lane == 0) {
                 mbar_arrive_cluster(oempty);
                 if (p.h_next) red_release_gpu_add(xflag + side, 1);
             }
+#ifdef OFX_DEBUG
+            prof_acc[6] += clock64() - drain_t0;
+#endif
         }
+        if (q == 0) PROF_DUMP(16 + 8 * wg);
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;" ::: "memory");
-        // ------------------------------------------------------------ LayerNorm warps
-        // (1) prologue: LN2 of this tile's x rows -> H (bf16, swizzled K-major operand layout); both pairs of the
-        //     group normalise the same rows (each needs them as its GEMM 1 operand);
-        // (2) in the idle time that follows, LN1 of the NEXT layer on the PREVIOUS tile's new rows -> h_next: the
-        //     two pairs wrote 256 columns each, so the rows are complete once both sides' 8 epilogue warps have
-        //     counted in; side s normalises rows s*64 .. +63 of each CTA's 128.
+        // ------------------------------------------------------------ LayerNorm warps (128 registers, no setmaxnreg)
+        // (1) LN2 of the NEXT tile's x rows -> hbuf (bf16, row-major, global / L2): one tile ahead of its use, so the
+        //     128 KB operand tile arrives in H by one bulk load the moment GEMM 1 of the running tile has retired
+        //     (computing it in place after h_empty left the tensor pipe idle for ~20k cycles per tile);
+        // (2) LN1 of the NEXT layer on the PREVIOUS tile's new rows -> h_next: the two pairs wrote 256 columns each,
+        //     so the rows are complete once both sides' 8 epilogue warps have counted in; side s normalises rows
+        //     s*64 .. +63 of each CTA's 128.
         const int lw = warp - LN_WARP0;
-        const uint32_t hfull = mapa_shared(smem_u32(h_full), 0);
-        uint32_t tphase = 0;
         int tiles_done = 0;
+        PROF_DECL();
         auto load_affine = [&](const float* gw, const float* gb, float4 (&g)[4], float4 (&be)[4]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -539,6 +690,25 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
                 for (int i = 0; i < 4; ++i)
                     v[u][i] = row + u < n_rows ? ldg128(p.x + (row + u) * DM + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
+        // LN2 of tile t's rows (this warp's 32 of the CTA's 128) -> hbuf[parity]
+        auto stage = [&](int t, int parity) {
+            float4 gam[4], bet[4];
+            load_affine(p.ln_w, p.ln_b, gam, bet);
+            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 32;
+            __nv_bfloat16* dst = p.hbuf + (static_cast<long long>(blockIdx.x) * 2 + parity) * ROWS * DM + static_cast<long long>(lw) * 32 * DM;
+#pragma unroll 1
+            for (int rb = 0; rb < 32; rb += 4) {
+                float4 v[4][4];
+                load4(v, row0 + rb);
+                norm4(v, gam, bet, [&](int u, int i, float y0, float y1, float y2, float y3) {
+                    if (row0 + rb + u >= n_rows) y0 = y1 = y2 = y3 = 0.f;
+                    *reinterpret_cast<uint2*>(dst + (rb + u) * DM + i * 128 + lane * 4) = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+                });
+            }
+            fence_proxy_async_all();      // generic-proxy global writes -> the producer's bulk loads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_staged);
+        };
         auto ln_next = [&](int t) {      // LN1(next layer) of tile t's new rows -> h_next
             float4 gam[4], bet[4];
             load_affine(p.lnn_w, p.lnn_b, gam, bet);
@@ -561,48 +731,20 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
                 });
             }
         };
-        int prev = -1;
-        for (int t = group; t < n_tiles; t += n_groups) {
-            const long long row0 = static_cast<long long>(t) * TILE + rank * ROWS + lw * 32;
-            // pull this warp's 32 rows (64 KB) towards L2 while the previous tile still owns H
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const long long off = (row0 * DM + (i * 32 + lane) * 32);   // 128-byte lines
-                if (row0 + (i * 32 + lane) / 16 < n_rows)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + off));
+        int ti = 0;
+        if (group < n_tiles) PROF(1, stage(group, 0));
+        for (int t = group; t < n_tiles; t += n_groups, ++ti) {
+            // the next tile goes into the other half of hbuf; its previous tenant (tile ti - 1) has been pulled into H
+            // and consumed once the producer has started on tile ti (hbuf_free: one arrival per use of a half, so the
+            // wait can never fall two phases behind)
+            if (t + n_groups < n_tiles) {
+                if (ti >= 1) PROF(0, bar_wait(&hbuf_free[(ti + 1) & 1], ((ti - 1) >> 1) & 1, "hbuf_free", t));
+                PROF(1, stage(t + n_groups, (ti + 1) & 1));
             }
-            float4 gam[4], bet[4];
-            load_affine(p.ln_w, p.ln_b, gam, bet);
-            auto emit_h = [&](int rbase) {
-                return [&, rbase](int u, int i, float y0, float y1, float y2, float y3) {
-                    const int r = lw * 32 + rbase + u;      // row within this CTA's 128
-                    if (row0 + rbase + u >= n_rows) y0 = y1 = y2 = y3 = 0.f;
-                    // element e = i*128 + lane*4: k-block e/64, 16-byte chunk (e%64)/8, 8-byte half
-                    const int kb = i * 2 + (lane >> 4);
-                    const int c16 = (lane & 15) >> 1;
-                    sts64(smem_u32(s_h) + kb * KBLK_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4) + (lane & 1) * 8,
-                          make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3)));
-                };
-            };
-            // 4-row batches, double-buffered: the loads of the next batch are in flight while this one is normalised
-            float4 va[4][4], vb[4][4];
-            load4(va, row0);                    // the first rows travel while GEMM 1 of the previous tile still reads H
-            bar_wait(h_empty, tphase ^ 1, "h_empty", t);     // GEMM 1 of the previous tile has consumed H
-            tphase ^= 1;
-#pragma unroll 1
-            for (int rb = 0; rb < 32; rb += 8) {
-                load4(vb, row0 + rb + 4);
-                norm4(va, gam, bet, emit_h(rb));
-                if (rb + 8 < 32) load4(va, row0 + rb + 8);
-                norm4(vb, gam, bet, emit_h(rb + 4));
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(hfull);
-            if (p.h_next && prev >= 0) { ++tiles_done; ln_next(prev); }
-            prev = t;
+            if (p.h_next && ti >= 1) { ++tiles_done; PROF(2, ln_next(t - n_groups)); }
         }
-        if (p.h_next && prev >= 0) { ++tiles_done; ln_next(prev); }
+        if (p.h_next && ti >= 1) { ++tiles_done; PROF(2, ln_next(group + (ti - 1) * n_groups)); }
+        if (lw == 0 && rank == 1) PROF_DUMP(8);
     }
     tc_fence_before();
     __syncthreads();
@@ -622,12 +764,16 @@ static size_t ffn2_scratch_bytes(int n_groups) {
 constexpr int kFlagsPerGroup = 4 * ffn2::NSLOT + 2 + 4;
 static size_t ffn2_flag_bytes(int n_groups) { return align_up(static_cast<size_t>(n_groups) * kFlagsPerGroup * sizeof(int), 256); }
 
+static size_t ffn2_hbuf_bytes(int n_groups) { return static_cast<size_t>(n_groups) * 4 * 2 * ffn2::ROWS * ffn2::DM * 2; }
+
 size_t ffn_block2_workspace_bytes(int sm) {
     const int n_groups = sm / 4;
-    return align_up(ffn2_scratch_bytes(n_groups), 256) + ffn2_flag_bytes(n_groups);
+    return align_up(ffn2_scratch_bytes(n_groups), 256) + ffn2_flag_bytes(n_groups) + align_up(ffn2_hbuf_bytes(n_groups), 256);
 }
 
-bool ffn_block2_supported(int dm, int fp) { return dm == ffn2::DM && fp > 0 && fp % 256 == 0 && sm_count() >= 4; }
+bool ffn_block2_supported(int dm, int fp) {
+    return dm == ffn2::DM && fp > 0 && fp % 256 == 0 && fp / 256 * 2 <= ffn2::NSLOT && sm_count() >= 4;
+}
 
 int ffn_block2_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
     using namespace ffn2;
@@ -648,6 +794,9 @@ int ffn_block2_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
     const uint64_t srows = static_cast<uint64_t>(n_groups_max) * 4 * NSLOT * ROWS;
     OFX_TRY(make_tmap_bf16(&tm_ust, ws, srows, CH, CH, 32));
     OFX_TRY(make_tmap_bf16(&tm_uld, ws, srows, CH, CH, 128));
+    uint8_t* hbuf = ws + align_up(ffn2_scratch_bytes(n_groups_max), 256) + ffn2_flag_bytes(n_groups_max);
+    CUtensorMap tm_h;
+    OFX_TRY(make_tmap_bf16(&tm_h, hbuf, static_cast<uint64_t>(n_groups_max) * 4 * 2 * ROWS, DM, DM, 128));
     static DeviceOnce configured;
     if (configured.need())
         OFX_CUDA(cudaFuncSetAttribute(ffn_block2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -656,9 +805,41 @@ int ffn_block2_bf16(const FfnBlockArgs& a, cudaStream_t stream) {
     OFX_CUDA(cudaMemsetAsync(flags, 0, ffn2_flag_bytes(n_groups_max), stream));
     Params p{a.x, a.rows, a.rows_dev, a.ln_w, a.ln_b, a.b1, a.b2, a.fp / 256,
              static_cast<__nv_bfloat16*>(a.h_next), a.lnn_w, a.lnn_b,
-             flags, flags + n_groups_max * 4 * NSLOT, flags + n_groups_max * (4 * NSLOT + 2)};
-    ffn_block2_kernel<<<groups * 4, NTHREADS, SMEM_BYTES, stream>>>(tm_w1, tm_w2, tm_ust, tm_uld, p);
+             flags, flags + n_groups_max * 4 * NSLOT, flags + n_groups_max * (4 * NSLOT + 2),
+             reinterpret_cast<__nv_bfloat16*>(ws), reinterpret_cast<__nv_bfloat16*>(hbuf), nullptr, 0};
+#ifdef OFX_DEBUG
+    { static int mode = -1; if (mode < 0) { const char* e = getenv("OFX_FFN2_MODE"); mode = e ? atoi(e) : 0; } p.mode = mode; }
+#endif
+#ifdef OFX_DEBUG   // instrumented builds only: per-role wait-cycle counters, dumped synchronously (OFX_FFN_PROF=1)
+    static int prof_on = -1;
+    static long long* prof_dev = nullptr;
+    if (prof_on < 0) { const char* e = getenv("OFX_FFN_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
+    if (prof_on) {
+        if (!prof_dev) OFX_CUDA(cudaMalloc(&prof_dev, 8 * 32 * 160));
+        OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 32 * 160, stream));
+        p.prof = prof_dev;
+    }
+#endif
+    ffn_block2_kernel<<<groups * 4, NTHREADS, SMEM_BYTES, stream>>>(tm_w1, tm_w2, tm_ust, tm_uld, tm_h, p);
     OFX_LAUNCH_CHECK();
+#ifdef OFX_DEBUG
+    if (prof_on) {
+        static int dumps = 0;
+        static long long h[32 * 160];
+        OFX_CUDA(cudaStreamSynchronize(stream));
+        OFX_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        if (dumps++ < 3)
+            for (int c = 0; c < groups * 4 && c < 148; c += 36) {
+                const long long* o = h + c * 32;
+                fprintf(stderr, "ffn2 prof cta %3d: producer total %lld  w_empty %lld  peer_flag %lld | %s total %lld  a %lld  b %lld  c %lld  d %lld\n",
+                        c, o[0], o[1], o[2], (c & 1) ? "LN warp: (h_empty, prologue, ln_next)" : "MMA: (w_full, u_full, h_full, out_empty)",
+                        o[8], o[9], o[10], o[11], o[12]);
+                for (int w = 0; w < 2; ++w)
+                    fprintf(stderr, "   epilogue wg %d: total %lld  acc1_full %lld  stg_read %lld  uack %lld  publish %lld  mish_chunks(all) %lld  out_full %lld  drain %lld\n",
+                            w, o[16 + 8 * w], o[17 + 8 * w], o[18 + 8 * w], o[19 + 8 * w], o[20 + 8 * w], o[21 + 8 * w], o[22 + 8 * w], o[23 + 8 * w]);
+            }
+    }
+#endif
     return OFX_OK;
 }
 

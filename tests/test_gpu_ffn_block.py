@@ -74,8 +74,8 @@ def test_ffn_block_rejects_other_shapes():
     assert _lib.lib().ofx_ffn_block_workspace_bytes(4, 1024, 2048) == 0
     x = torch.zeros(4, 512, device="cuda")
     rc = _lib.lib().ofx_ffn_block_bf16(x.data_ptr(), 4, 512, 2048, x.data_ptr(), x.data_ptr(), x.data_ptr(),
-                                       x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 256, None)
-    assert rc == -5         # workspace too small
+                                       x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, None)
+    assert rc == -5         # workspace too small (checked before anything is launched)
 
 
 @pytest.mark.parametrize("rows", [1, 64, 129, 257, 1000, 128 * 74 + 5, 128 * 74 * 3 + 77])

@@ -1,0 +1,37 @@
+"""Times HostScoringPipeline on configs[1] from pinned host buffers: padded (B,16,dpm) tensors against the packed
+valid-rows layout, and where the step's time goes (copies alone, scoring alone)."""
+import os, sys, time, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from outfitx_b200.pipeline import HostScoringPipeline, pack_valid_rows
+dev = torch.device("cuda", 0)
+model, sd = bench.make_model(dev)
+B = 8192
+img, txt, mask, text, cand, lengths = bench.make_cp_inputs(B, dev, seed=1000)
+host = {k: v.cpu().pin_memory() for k, v in dict(img=img, txt=txt, mask=mask, text=text, cand=cand).items()}
+ir, tr, lens = pack_valid_rows(host["img"], host["txt"], host["mask"])
+ir, tr = ir.pin_memory(), tr.pin_memory()
+def t(fn, n=10):
+    for _ in range(2): fn()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(n): fn()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
+for chunk in (1024, 2048, 4096):
+    pipe = HostScoringPipeline(model, chunk=chunk)
+    a = t(lambda: pipe.score(host["img"], host["txt"], host["mask"], host["text"], host["cand"]))
+    b = t(lambda: pipe.score_packed(ir, tr, lens, host["text"], host["cand"]))
+    print(f"chunk {chunk}: padded {a:.2f} ms ({B/a*1e3:,.0f}/s)   packed {b:.2f} ms ({B/b*1e3:,.0f}/s)", flush=True)
+# pieces
+dst = torch.empty_like(ir, device=dev)
+print(f"H2D of the packed rows of one modality ({ir.numel()*4/1e6:.0f} MB): {t(lambda: dst.copy_(ir, non_blocking=True)):.2f} ms")
+dst2 = torch.empty_like(host['img'], device=dev)
+print(f"H2D of the padded tensor of one modality ({host['img'].numel()*4/1e6:.0f} MB): {t(lambda: dst2.copy_(host['img'], non_blocking=True)):.2f} ms")
+t0 = time.perf_counter()
+for _ in range(20):
+    lens64 = lens.to(torch.int64); off = torch.zeros(B + 1, dtype=torch.int64); torch.cumsum(lens64, 0, out=off[1:])
+print(f"host-side collate arithmetic: {(time.perf_counter()-t0)/20*1e3:.3f} ms")
+import cProfile, pstats
+pipe = HostScoringPipeline(model, chunk=2048)
+pr = cProfile.Profile(); pr.enable()
+for _ in range(5): pipe.score_packed(ir, tr, lens, host["text"], host["cand"])
+pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
