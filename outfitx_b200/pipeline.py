@@ -34,7 +34,13 @@ class HostScoringPipeline:
     the copies to be asynchronous; pageable tensors work but serialise.
     """
 
-    def __init__(self, model, chunk: int = 2048):
+    def __init__(self, model, chunk: int = 2048, use_graphs: bool = True):
+        """``use_graphs``: the packed path replays one CUDA graph per (staging slot, chunk size) instead of issuing the
+        ~120 launches of a CP + FITB pass one by one -- at 2048 outfits per chunk the host needed as long to issue a
+        chunk as the GPU to run it.  Same kernels, same arguments (the staging buffers are persistent), same bits."""
+        self.use_graphs = use_graphs
+        self.tail_min = chunk      # smallest chunk of a tapered tail (see _plan); = chunk: uniform chunks
+        self._graphs = {}
         if chunk < 1:
             raise ValueError("chunk must be >= 1")
         self.model, self.chunk = model, chunk
@@ -44,10 +50,33 @@ class HostScoringPipeline:
         self.dev = dev
         self.copy_stream = torch.cuda.Stream(dev)
         self.compute_stream = torch.cuda.Stream(dev)
-        self._slots = [dict(), dict()]          # device staging buffers, two in flight
-        self._free = [torch.cuda.Event(), torch.cuda.Event()]   # slot may be overwritten
-        self._ready = [torch.cuda.Event(), torch.cuda.Event()]  # slot's copies have landed
+        # device staging buffers.  Four, not two: with a tapered tail the copy of chunk i must not wait for the scoring
+        # of chunk i - 2 (the step is copy-bound: every stall of the copy engine is added to it)
+        self.n_slots = 4
+        self._slots = [dict() for _ in range(self.n_slots)]
+        self._free = [torch.cuda.Event() for _ in range(self.n_slots)]    # slot may be overwritten
+        self._ready = [torch.cuda.Event() for _ in range(self.n_slots)]   # slot's copies have landed
         self._host = {}                          # pinned scratch for the ids / masks derived from lengths
+
+    def _plan(self, batch: int, taper: bool):
+        """Chunk boundaries [(lo, hi)]: uniform chunks, optionally with a tail cut into halves down to ``tail_min``.
+        Measured on configs[1] (tools/time_e2e.py, 8192 outfits, graphs on): every chunk costs ~0.6-1 ms on top of its
+        share of the work (a CP + FITB pass is ~120 kernels whose prologues / tails do not shrink with the batch), and
+        PCIe delivers ~43 GB/s while the scoring kernels run (55 GB/s alone), so 4 chunks of 2048 (12.1 ms) beat both
+        a tapered tail (2048 x 3 + 1024 x 2: 13.3 ms, ... + 512 x 2: 14.6 ms) and fewer, larger chunks."""
+        out, lo = [], 0
+        while batch - lo > self.chunk:
+            out.append((lo, lo + self.chunk))
+            lo += self.chunk
+        rest = batch - lo
+        if taper:
+            while rest > self.tail_min:
+                half = max(self.tail_min, (rest // 2 + 127) // 128 * 128)
+                out.append((lo, lo + half))
+                lo, rest = lo + half, rest - half
+        if rest > 0:
+            out.append((lo, lo + rest))
+        return out
 
     def _stage(self, slot: int, name: str, src: torch.Tensor) -> torch.Tensor:
         buf = self._slots[slot].get(name)
@@ -98,9 +127,9 @@ class HostScoringPipeline:
         self.compute_stream.wait_stream(cur)
         for i, lo in enumerate(range(0, B, self.chunk)):
             hi = min(B, lo + self.chunk)
-            s = i & 1
+            s = i % self.n_slots
             with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
+                if i >= self.n_slots:
                     self.copy_stream.wait_event(self._free[s])
                 d = {"mask": self._stage(s, "mask", outfit_mask[lo:hi])}
                 d["img"] = self._stage(s, "img", image_embeddings[lo:hi])
@@ -153,18 +182,20 @@ class HostScoringPipeline:
         mask_h = self._pinned("mask", (B, max_items), torch.bool)
         torch.ge(slot[None, :], lens[:, None], out=mask_h)
         ids_h = self._pinned("ids", (B, max_items), torch.int32)
-        chunk_base = off[torch.arange(0, B, self.chunk)].repeat_interleave(self.chunk)[:B]     # first row of each outfit's chunk
+        plan = self._plan(B, taper=self.use_graphs)
+        starts = torch.tensor([lo for lo, _ in plan], dtype=torch.int64)
+        sizes = torch.tensor([hi - lo for lo, hi in plan], dtype=torch.int64)
+        chunk_base = off[starts].repeat_interleave(sizes)             # first row of each outfit's chunk
         ids_h.copy_((off[:B, None] - chunk_base[:, None] + slot[None, :]).to(torch.int32))
         cap_rows = self.chunk * max_items
         cur = torch.cuda.current_stream(self.dev)
         self.copy_stream.wait_stream(cur)
         self.compute_stream.wait_stream(cur)
-        for i, lo in enumerate(range(0, B, self.chunk)):
-            hi = min(B, lo + self.chunk)
+        for i, (lo, hi) in enumerate(plan):
             r0, r1 = int(off[lo]), int(off[hi])
-            s = i & 1
+            s = i % self.n_slots
             with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
+                if i >= self.n_slots:
                     self.copy_stream.wait_event(self._free[s])
                 d = {"mask": self._stage(s, "pmask", mask_h[lo:hi]), "ids": self._stage(s, "pids", ids_h[lo:hi]),
                      "img": self._stage_rows(s, "pimg", image_rows[r0:r1], cap_rows),
@@ -175,15 +206,39 @@ class HostScoringPipeline:
                 self._ready[s].record(self.copy_stream)
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(self._ready[s])
-                # the chunk's rows are the "table" of the device-side collate; an empty chunk still needs one row
-                img_t = d["img"] if r1 > r0 else self._slots[s]["pimg"][:1]
-                txt_t = d["txt"] if r1 > r0 else self._slots[s]["ptxt"][:1]
-                enc = {"image_embeddings": img_t, "text_embeddings": txt_t, "item_ids": d["ids"]}
-                probs = self.model.score_cp(outfit_mask=d["mask"], encoder_input_dict=enc)
+                # the slot's row buffers are the "table" of the device-side collate (ids never point past the chunk's rows)
+                enc = {"image_embeddings": self._slots[s]["pimg"], "text_embeddings": self._slots[s]["ptxt"], "item_ids": d["ids"]}
+
+                def run():
+                    probs = self.model.score_cp(outfit_mask=d["mask"], encoder_input_dict=enc)
+                    pred = None
+                    if fitb:
+                        pred, _, _ = self.model.score_fitb(outfit_mask=d["mask"], target_item_text_embedding=d["text"],
+                                                           candidate_item_embedding=d["cand"], encoder_input_dict=enc)
+                    return probs, pred
+
+                key = (s, hi - lo, fitb, tuple(image_rows.shape[1:]), image_rows.dtype,
+                       tuple(candidate_item_embedding.shape[1:]) if fitb else None)
+                entry = self._graphs.get(key) if self.use_graphs else None
+                if entry is not None and entry[0] is not None:
+                    entry[0].replay()
+                    probs, pred = entry[1], entry[2]
+                else:
+                    probs, pred = run()
+                    if self.use_graphs and entry is None:
+                        # first time this (slot, chunk size) is seen: the eager pass above was the warm-up; capture the
+                        # same calls on the same persistent buffers for the following steps
+                        try:
+                            g = torch.cuda.CUDAGraph()
+                            self.compute_stream.synchronize()
+                            with torch.cuda.graph(g, stream=self.compute_stream):
+                                gp, gq = run()
+                            self._graphs[key] = (g, gp, gq)
+                        except Exception:
+                            self._graphs[key] = (None, None, None)      # not capturable here: stay eager
+                            torch.cuda.synchronize(self.dev)
                 out["probs"][lo:hi].copy_(probs, non_blocking=True)
                 if fitb:
-                    pred, _, _ = self.model.score_fitb(outfit_mask=d["mask"], target_item_text_embedding=d["text"],
-                                                       candidate_item_embedding=d["cand"], encoder_input_dict=enc)
                     out["pred"][lo:hi].copy_(pred, non_blocking=True)
                 self._free[s].record(self.compute_stream)
         cur.wait_stream(self.compute_stream)
@@ -214,9 +269,9 @@ class HostScoringPipeline:
         self.compute_stream.wait_stream(cur)
         for i, lo in enumerate(range(0, B, self.chunk)):
             hi = min(B, lo + self.chunk)
-            s = i & 1
+            s = i % self.n_slots
             with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
+                if i >= self.n_slots:
                     self.copy_stream.wait_event(self._free[s])
                 d = {"ids": self._stage(s, "ids", item_ids[lo:hi]), "mask": self._stage(s, "idmask", outfit_mask[lo:hi])}
                 if fitb:

@@ -104,6 +104,19 @@ def test_packed_host_layout_equals_padded():
         got = HostScoringPipeline(m, chunk=chunk).score_packed(rows[0], rows[1], lens, pinned[3] if pin else pageable[3],
                                                                pinned[4] if pin else pageable[4])
         assert torch.equal(got["probs"], want["probs"]) and torch.equal(got["pred"], want["pred"])
+    # the same pipeline object again and again: the first call runs eagerly and captures one CUDA graph per staging
+    # slot, the following calls replay them -- on different data each time (the graphs must not have baked values in)
+    pipe = HostScoringPipeline(m, chunk=64)
+    eager = HostScoringPipeline(m, chunk=64, use_graphs=False)
+    for rep in range(3):
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(rep))
+        pg = [t[perm].contiguous() for t in pageable]
+        ir, tr, ln = pack_valid_rows(pg[0], pg[1], pg[2])
+        a = pipe.score_packed(ir, tr, ln, pg[3], pg[4])
+        b = eager.score_packed(ir, tr, ln, pg[3], pg[4])
+        assert torch.equal(a["probs"], b["probs"]) and torch.equal(a["pred"], b["pred"])
+        assert torch.equal(a["probs"], want["probs"][perm]) and torch.equal(a["pred"], want["pred"][perm])
+    assert any(e[0] is not None for e in pipe._graphs.values())        # graphs really were captured and replayed
     cp_only = HostScoringPipeline(m, chunk=128).score_packed(img_rows, txt_rows, lens)
     assert torch.equal(cp_only["probs"], want["probs"]) and "pred" not in cp_only
     with pytest.raises(ValueError):

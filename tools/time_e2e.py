@@ -16,7 +16,11 @@ def t(fn, n=10):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(n): fn()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
-for chunk in (1024, 2048, 4096):
+for chunk, tail in ((2048, 2048), (2048, 1024), (2048, 512), (1536, 1536), (1536, 768), (3072, 1024), (2560, 2560)):
+    pipe = HostScoringPipeline(model, chunk=chunk); pipe.tail_min = tail
+    b = t(lambda: pipe.score_packed(ir, tr, lens, host["text"], host["cand"]))
+    print(f"chunk {chunk} tail_min {tail}: plan {[hi - lo for lo, hi in pipe._plan(B, True)]}  packed {b:.2f} ms ({B/b*1e3:,.0f}/s)", flush=True)
+for chunk in (2048,):
     pipe = HostScoringPipeline(model, chunk=chunk)
     a = t(lambda: pipe.score(host["img"], host["txt"], host["mask"], host["text"], host["cand"]))
     b = t(lambda: pipe.score_packed(ir, tr, lens, host["text"], host["cand"]))
