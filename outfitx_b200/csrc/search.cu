@@ -59,6 +59,8 @@ struct SchedSearch {
         int* progress; // [n_units] tile index each unit's producer has reached (-1 not started, huge = done), or null
         int window;    // a unit may run at most `window` tiles ahead of the slowest co-scheduled unit of its segment
         int check;     // pacing check every `check` tiles (power of two)
+        int lead;      // bit 0: the first unit of a round also prefetches (its segment's group 0 ran a round earlier);
+                       // bit 1: the last pf_dist tiles of a unit prefetch the head of the segment its CTA leads next
     };
     static constexpr bool kPrefetch = true;
     static constexpr bool kThrottle = true;
@@ -155,7 +157,16 @@ struct SchedSearch {
             // pf_dist tiles ahead, so that the other groups (and group 0 itself) hit L2 and each
             // gallery tile crosses HBM once per segment sweep
             n0 = (seg_lo + it) * kSearchBN;
-            pf_n0 = (qg == 0 && it + p.pf_dist < seg_len) ? (seg_lo + it + p.pf_dist) * kSearchBN : -1;
+            const bool lead = qg == 0 || ((p.lead & 1) && unit % step == 0);
+            pf_n0 = (lead && it + p.pf_dist < seg_len) ? (seg_lo + it + p.pf_dist) * kSearchBN : -1;
+            if ((p.lead & 2) && it + p.pf_dist >= seg_len && unit + step < p.n_units) {
+                // nothing left to pull ahead in this segment: warm the first tiles of the segment this CTA
+                // leads in the next round, so that round does not start on pf_dist cold tiles
+                const int nu = unit + step, nseg = nu / p.n_qgroups;
+                const int j = it + p.pf_dist - seg_len;
+                if ((nu - nseg * p.n_qgroups == 0 || nu % step == 0) && nseg * p.seg_tiles + j < p.n_tiles)
+                    pf_n0 = (nseg * p.seg_tiles + j) * kSearchBN;
+            }
             return true;
         }
         const int sub = it / p.sub_tiles;
@@ -207,6 +218,54 @@ static SearchPlan make_plan(long long n_rows, int n_query, int n_sm) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Counting bound shared by all units of a query.
+// A unit's list only ever sees its own segment, so its admission gate settles at the kcap-th best of ~1/37 of the
+// shard: every (query, segment) pair fills a list from scratch and about one score in a thousand still passes the
+// gate -- half of all 32x32 slabs take the divergent insert path, and that, not the MMA, sets the pace of a short
+// segment (1.25 M-row shard: tensor pipe 72 % busy, ~120 us lost per unit).  The rows of different segments are
+// distinct rows, though: if c rows of the whole shard have been seen with a score >= T, the c-th best score of the
+// shard is >= T, whichever units saw them.  So every admitted candidate is also counted (one RED) in a 64-bucket
+// histogram of its query, buckets uniform over [lo, lo + 2.5 (top - lo)] with lo / top the kcap-th and the largest
+// of the seeding block maxima, and every few tiles a thread reads its query's histogram and raises its gate to
+//     min( T(kcap), T(k) - 2 eps )
+// T(c) = lower edge of the bucket where the count from the top reaches c.  T(kcap) keeps the lists at the kcap
+// best of the SHARD, and T(k) - 2 eps keeps the exactness certificate provable: T(k) <= the k-th best bf16 score
+// Sb_k, the k rows above it have exact scores >= Sb_k - eps, hence T_out <= Sb_k - 2 eps < S_k - eps.
+// HistQ = {lo, inv_w, w_safe, margin}: bucket(s) = trunc(fl(fl(s - lo) * inv_w)) clamped to [0, 63], and
+// w_safe = (1 / inv_w)(1 - 2e-6) rounded down, so lo + j * w_safe (rounded down) is below every score that can
+// land in bucket j or higher whatever the two roundings did.
+// ---------------------------------------------------------------------------------------
+constexpr int kHistBuckets = 64;
+constexpr int kHistRefresh = 8;     // tiles between two reads of the histogram (power of two)
+
+static __device__ __noinline__ void hist_count(uint32_t* __restrict__ h, const float4* __restrict__ hq, float s) {
+    const float4 q = __ldg(hq);
+    int b = static_cast<int>(__fmul_rn(__fsub_rn(s, q.x), q.y));
+    b = max(0, min(kHistBuckets - 1, b));
+    atomicAdd(h + b, 1u);
+}
+
+static __device__ __noinline__ float hist_bound(const uint32_t* __restrict__ h, const float4* __restrict__ hq, int m, int k) {
+    const float4 q = __ldg(hq);
+    unsigned cum = 0;
+    int jm = -1, jk = -1;
+    for (int b4 = kHistBuckets / 4 - 1; b4 >= 0 && jm < 0; --b4) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(h) + b4);
+        const unsigned c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 3; u >= 0; --u) {
+            cum += c[u];
+            if (jk < 0 && cum >= static_cast<unsigned>(k)) jk = 4 * b4 + u;
+            if (jm < 0 && cum >= static_cast<unsigned>(m)) jm = 4 * b4 + u;
+        }
+    }
+    if (jm < 0) return q.x;      // fewer than m rows counted so far: the seeded bound stands
+    const float tm = __fadd_rd(q.x, __fmul_rd(static_cast<float>(jm), q.z));
+    const float tk = __fsub_rd(__fadd_rd(q.x, __fmul_rd(static_cast<float>(jk), q.z)), q.w);
+    return fmaxf(q.x, fminf(tm, tk));
+}
+
+// ---------------------------------------------------------------------------------------
 // Fused top-K' epilogue.  Thread <-> accumulator row <-> query.  List slot j of thread t is
 // ls[j * 128 + t] / li[j * 128 + t] (conflict-free across a warp).
 // ---------------------------------------------------------------------------------------
@@ -220,6 +279,9 @@ struct EpiTopK {
         int* cand_i;               // [n_units][128][KCAP] shard-local row ids
         int* cand_n;               // [n_units][128]
         int* progress;             // [n_units] scheduler pacing state (see SchedSearch::throttle), not used by the epilogue
+        uint32_t* hist;            // [n_query][kHistBuckets] counting bound (see above), or null
+        const float4* hq;          // [n_query] HistQ
+        int k;
     };
     static constexpr int kSmemBytes = KCAP * 128 * 8;
     static constexpr int kWarps = 4;
@@ -227,14 +289,15 @@ struct EpiTopK {
     float* ls;
     int* li;
     int cnt, lpos, lidx;
-    float lmin, thr;  // gate: s >= thr (thr = global threshold until the list is full, then its minimum)
+    float lmin, thr;  // gate: s >= thr (thr = max(shared bound, list minimum once the list is full))
+    float gthr;       // the shared bound: thr_enc / counting bound as last read
     bool full;
 
     __device__ void begin(const Params&, const SchedSearch&, int quarter, int lane, uint8_t* smem) {
         const int t = quarter * 32 + lane;
         ls = reinterpret_cast<float*>(smem) + t;
         li = reinterpret_cast<int*>(smem + KCAP * 128 * 4) + t;
-        cnt = 0; lpos = 0; lidx = 0; lmin = 0.f; thr = -INFINITY; full = false;
+        cnt = 0; lpos = 0; lidx = 0; lmin = 0.f; thr = -INFINITY; gthr = -INFINITY; full = false;
     }
 
     __device__ void end(const Params&, int) {}
@@ -258,7 +321,7 @@ struct EpiTopK {
         lmin = r.x;
         lpos = __float_as_int(r.y);
         lidx = __float_as_int(r.z);
-        thr = r.x;
+        thr = fmaxf(r.x, gthr);
     }
 
     // Tiles of a unit arrive in rotated order, so ties are resolved on the index explicitly:
@@ -279,10 +342,20 @@ struct EpiTopK {
                          int lane, uint8_t*) {
         const int row = s.m0 + quarter * 32 + lane;
         const bool live = row < p.n_query;
+        uint32_t* const hrow = p.hist ? p.hist + static_cast<size_t>(row) * kHistBuckets : nullptr;
         if (s.first) {
             cnt = 0;
             full = false;
-            thr = live ? dec_score(__ldcg(p.thr_enc + row)) : INFINITY;
+            gthr = live ? dec_score(__ldcg(p.thr_enc + row)) : INFINITY;
+            thr = gthr;
+        }
+        if (hrow && live && (s.first || (s.it & (kHistRefresh - 1)) == 0)) {
+            // every gate a row can be dropped at is folded into thr_enc (the certificate's T_out)
+            const float t = hist_bound(hrow, p.hq + row, KCAP, p.k);
+            const float g = dec_score(__ldcg(p.thr_enc + row));
+            if (t > g) atomicMax(p.thr_enc + row, enc_score(t));
+            gthr = fmaxf(gthr, fmaxf(t, g));
+            thr = fmaxf(thr, gthr);
         }
         const long long col_lim = p.n_rows - s.n0;  // columns >= col_lim are padding
 #pragma unroll 1
@@ -306,7 +379,10 @@ struct EpiTopK {
                     if (m4[qd] >= thr) {
 #pragma unroll
                         for (int i = qd; i < 32; i += 4) {
-                            if (v[i] >= thr && c + i < col_lim) insert(v[i], s.n0 + c + i);
+                            if (v[i] >= thr && c + i < col_lim) {
+                                if (hrow) hist_count(hrow, p.hq + row, v[i]);
+                                insert(v[i], s.n0 + c + i);
+                            }
                         }
                     }
                 }
@@ -342,6 +418,7 @@ struct EpiBlockMax {
         uint32_t* thr_enc;
         int m;                     // which order statistic of the block maxima (= list capacity of the main sweep)
         int* progress;             // scheduler pacing state (SchedSearch::throttle)
+        uint32_t* top_enc;         // [n_query] largest block maximum (upper end of the counting histogram), or null
     };
     static constexpr int kMaxBlocks = NBMAX;
     static constexpr int kSmemBytes = kMaxBlocks * 128 * 4;
@@ -379,7 +456,7 @@ struct EpiBlockMax {
         if (s.last) {
             const int n = min(nb, kMaxBlocks);
             if (n >= p.m && row < p.n_query) {
-                float kth = -INFINITY;
+                float kth = -INFINITY, top = -INFINITY;
                 for (int r = 0; r < p.m; ++r) {          // m-th largest by repeated extraction (warp-uniform trip counts)
                     float mx = -INFINITY;
                     int mp = 0;
@@ -388,9 +465,11 @@ struct EpiBlockMax {
                         if (v > mx) { mx = v; mp = j; }
                     }
                     kth = mx;
+                    if (r == 0) top = mx;
                     ls[mp * 128] = -INFINITY;
                 }
                 if (kth > -INFINITY) atomicMax(p.thr_enc + row, enc_score(kth));
+                if (p.top_enc) p.top_enc[row] = enc_score(top);
             }
         }
     }
@@ -488,6 +567,37 @@ __device__ __forceinline__ double bf16_score_error_bound(double qn, double half_
     double e = (2.0 * u + u * u + (dim + 64) * (1.0 / 4194304.0)) * qn * g * (1.0 + u) * (1.0 + u);
     if (metric == OFX_METRIC_L2) e += (1.0 / 262144.0 + dim * (1.0 / 16777216.0)) * half_g2;
     return e * 1.01;
+}
+
+// Per-query parameters of the counting bound (one warp per query; also clears the query's histogram).
+__global__ void __launch_bounds__(256)
+hist_setup_kernel(const float* __restrict__ queries, int n_query, int dim, int metric, const uint32_t* __restrict__ thr_enc,
+                  const uint32_t* __restrict__ top_enc, const float* __restrict__ max_half_sqnorm, float4* __restrict__ hq,
+                  uint32_t* __restrict__ hist) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= n_query) return;
+    double qq = 0.0;
+    for (int c = lane; c < dim; c += 32) {
+        const double v = static_cast<double>(__ldg(queries + static_cast<size_t>(q) * dim + c));
+        qq += v * v;
+    }
+    for (int o = 16; o; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    for (int b = lane; b < kHistBuckets; b += 32) hist[static_cast<size_t>(q) * kHistBuckets + b] = 0u;
+    if (lane) return;
+    const double eps = bf16_score_error_bound(sqrt(qq) * (1.0 + 1e-9), static_cast<double>(__ldg(max_half_sqnorm)), dim, metric);
+    const float lo = dec_score(thr_enc[q]), top = dec_score(top_enc[q]);
+    const float span = (top - lo) * (2.5f / kHistBuckets);
+    float4 r;
+    r.x = lo;
+    if (lo > -INFINITY && span > 0.f && span < INFINITY && 1.f / span < INFINITY) {
+        r.y = 1.f / span;
+        r.z = __double2float_rd((1.0 / static_cast<double>(r.y)) * (1.0 - 2e-6));
+    } else {             // degenerate sample (ties, infinities): every candidate counts in bucket 0, whose edge is lo
+        r.y = 0.f;
+        r.z = 0.f;
+    }
+    r.w = __double2float_ru(2.0 * eps * 1.001);
+    hq[q] = r;
 }
 
 __global__ void __launch_bounds__(kMergeThreads)
@@ -916,7 +1026,7 @@ static PackedGallery gallery_layout(long long n_rows, int dim) {
 }
 
 struct SearchWs {
-    size_t q_bf16, thr, cand_n, cand_s, cand_i, prog, total;
+    size_t q_bf16, thr, cand_n, cand_s, cand_i, prog, top, hq, hist, total;
     int kcap;
     SearchPlan plan;
 };
@@ -939,6 +1049,10 @@ static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     w.cand_s = take(slots * w.kcap * 4);
     w.cand_i = take(slots * w.kcap * 4);
     w.prog = take(static_cast<size_t>(w.plan.n_units) * 4);
+    const size_t q_pad = static_cast<size_t>(w.plan.n_qgroups) * w.plan.cl * 128;
+    w.top = take(q_pad * 4);
+    w.hq = take(q_pad * 16);
+    w.hist = take(q_pad * kHistBuckets * 4);
     w.total = o;
     return w;
 }
@@ -968,7 +1082,9 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     if (progress) OFX_CUDA(cudaMemsetAsync(progress, 0xFF, static_cast<size_t>(pl.n_units) * 4, stream));
     static int check = -1;      // OFX_SEARCH_CHECK: tiles between pacing checks (power of two)
     if (check < 0) { const char* e = getenv("OFX_SEARCH_CHECK"); check = e ? atoi(e) : 8; if (check < 1 || (check & (check - 1))) check = 8; }
-    SchedSearch::Params sp{pl.n_qgroups, pl.n_tiles, pl.seg_tiles, pl.n_units, pl.sub_tiles, CL, pf_dist, progress, window, check};
+    static int lead = -1;       // OFX_SEARCH_LEAD: prefetch-leader policy bits (SchedSearch::Params::lead)
+    if (lead < 0) { const char* e = getenv("OFX_SEARCH_LEAD"); lead = e ? atoi(e) : 3; }
+    SchedSearch::Params sp{pl.n_qgroups, pl.n_tiles, pl.seg_tiles, pl.n_units, pl.sub_tiles, CL, pf_dist, progress, window, check, lead};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pl.grid);
     cfg.blockDim = dim3(tc_threads<Epi>());
@@ -1107,11 +1223,16 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
             if (kWarmRows % 256) kWarmRows = warm_legacy ? 4096 : 8192;
         }
         const long long warm_rows = kWarmRows * (W.kcap / 32);    // 2 kcap blocks of 128 rows by default
+        static int use_hist = -1;       // OFX_SEARCH_HIST=0: no counting bound (A/B timing)
+        if (use_hist < 0) { const char* e = getenv("OFX_SEARCH_HIST"); use_hist = (e && e[0] == '0') ? 0 : 1; }
+        uint32_t* top = reinterpret_cast<uint32_t*>(ws + W.top);
+        float4* hq = nullptr;
+        uint32_t* hist = nullptr;
         if (kWarmRows > 0 && n_rows >= 16 * warm_rows) {
             if (warm_legacy) {
                 SearchPlan wp = make_plan(kWarmRows, n_query, sm_count());
                 if (W.kcap == 32 && wp.cl == W.plan.cl && wp.n_units <= W.plan.n_units) {
-                    EpiTopK<32>::Params ep{kWarmRows, n_query, thr, cand_s, cand_i, cand_n, prog};
+                    EpiTopK<32>::Params ep{kWarmRows, n_query, thr, cand_s, cand_i, cand_n, prog, nullptr, nullptr, k};
                     OFX_TRY((launch_search_cl<EpiTopK<32>, 4, 6>(q_bf16, n_query, pk, kWarmRows, wp, ep, dim, st)));
                 }
             } else if (warm_rows / 128 >= W.kcap) {
@@ -1123,25 +1244,33 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
                 const int n_cl = sm_count() / wp.cl;
                 wp.grid = (wp.n_units < n_cl ? wp.n_units : n_cl) * wp.cl;
                 if (W.kcap == 32) {
-                    EpiBlockMax<64>::Params ep{warm_rows, n_query, thr, 32, prog};
+                    EpiBlockMax<64>::Params ep{warm_rows, n_query, thr, 32, prog, top};
                     OFX_TRY((launch_search_cl<EpiBlockMax<64>, 4, 6>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
                 } else if (W.kcap == 64) {
-                    EpiBlockMax<128>::Params ep{warm_rows, n_query, thr, 64, prog};
+                    EpiBlockMax<128>::Params ep{warm_rows, n_query, thr, 64, prog, top};
                     OFX_TRY((launch_search_cl<EpiBlockMax<128>, 3, 5>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
                 } else {
-                    EpiBlockMax<256>::Params ep{warm_rows, n_query, thr, 128, prog};
+                    EpiBlockMax<256>::Params ep{warm_rows, n_query, thr, 128, prog, top};
                     OFX_TRY((launch_search_cl<EpiBlockMax<256>, 2, 3>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
+                }
+                if (use_hist) {       // every query has a seeded bound and a sample maximum: the counting bound can run
+                    hq = reinterpret_cast<float4*>(ws + W.hq);
+                    hist = reinterpret_cast<uint32_t*>(ws + W.hist);
+                    hist_setup_kernel<<<(n_query + 7) / 8, 256, 0, st>>>(queries, n_query, dim, metric, thr, top,
+                        reinterpret_cast<const float*>(pk + L.stats), hq, hist);
+                    OFX_LAUNCH_CHECK();
+                    count_launch();
                 }
             }
         }
         if (W.kcap == 32) {
-            EpiTopK<32>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
+            EpiTopK<32>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog, hist, hq, k};
             OFX_TRY((launch_search_cl<EpiTopK<32>, 4, 6>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         } else if (W.kcap == 64) {
-            EpiTopK<64>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
+            EpiTopK<64>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog, hist, hq, k};
             OFX_TRY((launch_search_cl<EpiTopK<64>, 3, 5>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         } else {
-            EpiTopK<128>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog};
+            EpiTopK<128>::Params ep{n_rows, n_query, thr, cand_s, cand_i, cand_n, prog, hist, hq, k};
             OFX_TRY((launch_search_cl<EpiTopK<128>, 2, 3>(q_bf16, n_query, pk, n_rows, W.plan, ep, dim, st)));
         }
     }

@@ -47,5 +47,7 @@ if not a.skip_cir:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.reps
-    print("search ms", ms, "TFLOP/s", 2.0 * a.queries * a.rows * 1024 / ms / 1e9)
+    from outfitx_b200.search import SearchStats
+    print("search ms", ms, "TFLOP/s", 2.0 * a.queries * a.rows * 1024 / ms / 1e9,
+          "uncertified", SearchStats.uncertified, "of", SearchStats.queries)
 print("ok")
