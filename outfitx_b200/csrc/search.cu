@@ -236,27 +236,27 @@ static SearchPlan make_plan(long long n_rows, int n_query, int n_sm) {
 // land in bucket j or higher whatever the two roundings did.
 // ---------------------------------------------------------------------------------------
 constexpr int kHistBuckets = 64;
-constexpr int kHistRefresh = 8;     // tiles between two reads of the histogram (power of two)
-
-static __device__ __noinline__ void hist_count(uint32_t* __restrict__ h, const float4* __restrict__ hq, float s) {
-    const float4 q = __ldg(hq);
-    int b = static_cast<int>(__fmul_rn(__fsub_rn(s, q.x), q.y));
-    b = max(0, min(kHistBuckets - 1, b));
-    atomicAdd(h + b, 1u);
-}
+constexpr int kSeedSegments = 4;   // sample segments of the seeding sweep (pooled block maxima)
+constexpr int kHistRefresh = 16;    // tiles between two reads of the histogram (power of two)
 
 static __device__ __noinline__ float hist_bound(const uint32_t* __restrict__ h, const float4* __restrict__ hq, int m, int k) {
     const float4 q = __ldg(hq);
     unsigned cum = 0;
     int jm = -1, jk = -1;
-    for (int b4 = kHistBuckets / 4 - 1; b4 >= 0 && jm < 0; --b4) {
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(h) + b4);
-        const unsigned c[4] = {v.x, v.y, v.z, v.w};
+    // two batches of eight 16-byte loads (all in flight together), upper half of the buckets first
+    for (int half = 1; half >= 0 && jm < 0; --half) {
+        uint4 v[8];
 #pragma unroll
-        for (int u = 3; u >= 0; --u) {
-            cum += c[u];
-            if (jk < 0 && cum >= static_cast<unsigned>(k)) jk = 4 * b4 + u;
-            if (jm < 0 && cum >= static_cast<unsigned>(m)) jm = 4 * b4 + u;
+        for (int j = 0; j < 8; ++j) v[j] = __ldcg(reinterpret_cast<const uint4*>(h) + half * 8 + j);
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            const unsigned c[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int u = 3; u >= 0; --u) {
+                cum += c[u];
+                if (jk < 0 && cum >= static_cast<unsigned>(k)) jk = 4 * (half * 8 + j) + u;
+                if (jm < 0 && cum >= static_cast<unsigned>(m)) jm = 4 * (half * 8 + j) + u;
+            }
         }
     }
     if (jm < 0) return q.x;      // fewer than m rows counted so far: the seeded bound stands
@@ -283,7 +283,7 @@ struct EpiTopK {
         const float4* hq;          // [n_query] HistQ
         int k;
     };
-    static constexpr int kSmemBytes = KCAP * 128 * 8;
+    static constexpr int kSmemBytes = KCAP * 128 * 8 + 1024;      // lists + {lo, inv_w} per thread
     static constexpr int kWarps = 4;
 
     float* ls;
@@ -338,18 +338,39 @@ struct EpiTopK {
         }
     }
 
+    // v[i] for a run-time i without spilling v[] to local memory: a 5-level select tree (31 selects)
+    static __device__ __forceinline__ float sel32(const float (&v)[32], int i) {
+        float a[16], b[8], c4[4];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = (i & 1) ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = (i & 2) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c4[j] = (i & 4) ? b[2 * j + 1] : b[2 * j];
+        const float d0 = (i & 8) ? c4[1] : c4[0], d1 = (i & 8) ? c4[3] : c4[2];
+        return (i & 16) ? d1 : d0;
+    }
+
     __device__ void tile(const Params& p, const SchedSearch& s, uint32_t t_acc, int quarter,
                          int lane, uint8_t*) {
         const int row = s.m0 + quarter * 32 + lane;
         const bool live = row < p.n_query;
         uint32_t* const hrow = p.hist ? p.hist + static_cast<size_t>(row) * kHistBuckets : nullptr;
+        float* const hp = reinterpret_cast<float*>(li + KCAP * 128);      // [2][128]: lo, inv_w of this thread's query
         if (s.first) {
             cnt = 0;
             full = false;
             gthr = live ? dec_score(__ldcg(p.thr_enc + row)) : INFINITY;
             thr = gthr;
+            if (hrow && live) {
+                const float4 q = __ldg(p.hq + row);
+                hp[0] = q.x;
+                hp[128] = q.y;
+            }
         }
-        if (hrow && live && (s.first || (s.it & (kHistRefresh - 1)) == 0)) {
+        // the first round learns the bound from scratch (it moves as kcap / rows seen): look four times as often
+        const int period = s.unit < s.step ? kHistRefresh / 4 : kHistRefresh;
+        if (hrow && live && (s.first || (s.it & (period - 1)) == 0)) {
             // every gate a row can be dropped at is folded into thr_enc (the certificate's T_out)
             const float t = hist_bound(hrow, p.hq + row, KCAP, p.k);
             const float g = dec_score(__ldcg(p.thr_enc + row));
@@ -370,19 +391,29 @@ struct EpiTopK {
 #pragma unroll
             for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
             const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-            if (mx >= thr) {
-                // Taken by the whole warp as soon as ONE of its 32 queries has a candidate in this
-                // slab (about half of all slabs over a sweep), so the path must be short: the four
-                // strided partial maxima say which 8 columns can hold candidates.
+            if (__any_sync(0xffffffffu, mx >= thr)) {
+                // Taken by the whole warp as soon as ONE of its 32 queries has a candidate in this slab.  Every lane
+                // builds the bit mask of its own candidates and the lanes then pop theirs TOGETHER: the trip count
+                // is the largest number of candidates any one query has in the slab (1, rarely 2), not the number
+                // of distinct columns with a candidate anywhere in the warp -- with cold lists (first round) that
+                // was 5-6 serialised insertions per slab.
+                uint32_t mask = 0;
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    if (m4[qd] >= thr) {
-#pragma unroll
-                        for (int i = qd; i < 32; i += 4) {
-                            if (v[i] >= thr && c + i < col_lim) {
-                                if (hrow) hist_count(hrow, p.hq + row, v[i]);
-                                insert(v[i], s.n0 + c + i);
+                for (int i = 0; i < 32; ++i) mask |= (v[i] >= thr) ? (1u << i) : 0u;
+                const long long room = col_lim - c;
+                if (room < 32) mask &= room <= 0 ? 0u : ((1u << static_cast<int>(room)) - 1u);
+                while (__any_sync(0xffffffffu, mask != 0u)) {
+                    if (mask) {
+                        const int i = __ffs(mask) - 1;
+                        mask &= mask - 1u;
+                        const float sv = sel32(v, i);
+                        if (sv >= thr) {          // thr may have risen with this lane's previous insertion
+                            if (hrow) {
+                                int b = static_cast<int>(__fmul_rn(__fsub_rn(sv, hp[0]), hp[128]));
+                                b = max(0, min(kHistBuckets - 1, b));
+                                atomicAdd(hrow + b, 1u);
                             }
+                            insert(sv, s.n0 + c + i);
                         }
                     }
                 }
@@ -404,7 +435,10 @@ struct EpiTopK {
 // ---------------------------------------------------------------------------------------
 // Threshold seeding epilogue.  For every query the maxima of NB disjoint blocks of 128 gallery rows are
 // NB scores of NB distinct rows, so the m-th largest of them is a lower bound of the m-th best score of
-// the whole gallery -- a valid starting threshold for the top-m lists of the main sweep.  Unlike running
+// the whole gallery -- a valid starting threshold for the top-m lists of the main sweep.  The sample is split
+// into as many segments as there are idle CTA pairs per query group (2 at 8192 queries, 4 at 4096): the units
+// only write their maxima, seed_finish_kernel takes the m-th largest of the POOL (64 -> 128 blocks moves the
+// bound from the 0.54 % to the 0.22 % quantile at the same wall time).  Unlike running
 // the real top-k epilogue over a sample (the previous warm-up: 1.15 ms at 8192 queries, dominated by
 // divergent list insertions while the lists are cold) this is one running maximum per thread and a
 // warp-uniform selection at the end: ~60 us for 64 blocks, and with NB = 2 m the bound (the median of
@@ -415,10 +449,9 @@ struct EpiBlockMax {
     struct Params {
         long long n_rows;          // rows swept (multiple of kSearchBN, all real)
         int n_query;
-        uint32_t* thr_enc;
-        int m;                     // which order statistic of the block maxima (= list capacity of the main sweep)
         int* progress;             // scheduler pacing state (SchedSearch::throttle)
-        uint32_t* top_enc;         // [n_query] largest block maximum (upper end of the counting histogram), or null
+        float* bm;                 // [n_query][nb_total] pooled block maxima, segment-major
+        int nb_seg, nb_total;      // blocks per sample segment, blocks of all segments
     };
     static constexpr int kMaxBlocks = NBMAX;
     static constexpr int kSmemBytes = kMaxBlocks * 128 * 4;
@@ -454,22 +487,13 @@ struct EpiBlockMax {
             ++nb;
         }
         if (s.last) {
+            // the unit's block maxima go to the query's pool (segment-major); seed_finish_kernel selects from the
+            // pooled maxima of all sample segments
             const int n = min(nb, kMaxBlocks);
-            if (n >= p.m && row < p.n_query) {
-                float kth = -INFINITY, top = -INFINITY;
-                for (int r = 0; r < p.m; ++r) {          // m-th largest by repeated extraction (warp-uniform trip counts)
-                    float mx = -INFINITY;
-                    int mp = 0;
-                    for (int j = 0; j < n; ++j) {
-                        const float v = ls[j * 128];
-                        if (v > mx) { mx = v; mp = j; }
-                    }
-                    kth = mx;
-                    if (r == 0) top = mx;
-                    ls[mp * 128] = -INFINITY;
-                }
-                if (kth > -INFINITY) atomicMax(p.thr_enc + row, enc_score(kth));
-                if (p.top_enc) p.top_enc[row] = enc_score(top);
+            if (row < p.n_query) {
+                const int seg = s.unit / s.p.n_qgroups;
+                float* out = p.bm + static_cast<size_t>(row) * p.nb_total + static_cast<size_t>(seg) * p.nb_seg;
+                for (int j = 0; j < p.nb_seg; ++j) out[j] = j < n ? ls[j * 128] : -INFINITY;
             }
         }
     }
@@ -569,23 +593,44 @@ __device__ __forceinline__ double bf16_score_error_bound(double qn, double half_
     return e * 1.01;
 }
 
-// Per-query parameters of the counting bound (one warp per query; also clears the query's histogram).
+// After the seeding sweep, one warp per query: the m-th largest of the pooled block maxima becomes the query's
+// starting threshold, and (hq != null) the parameters of the counting bound are set and its histogram cleared.
 __global__ void __launch_bounds__(256)
-hist_setup_kernel(const float* __restrict__ queries, int n_query, int dim, int metric, const uint32_t* __restrict__ thr_enc,
-                  const uint32_t* __restrict__ top_enc, const float* __restrict__ max_half_sqnorm, float4* __restrict__ hq,
-                  uint32_t* __restrict__ hist) {
+seed_finish_kernel(const float* __restrict__ queries, int n_query, int dim, int metric, const float* __restrict__ bm,
+                   int nb_total, int m, uint32_t* __restrict__ thr_enc, const float* __restrict__ max_half_sqnorm,
+                   float4* __restrict__ hq, uint32_t* __restrict__ hist) {
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= n_query) return;
+    // rank of every pooled maximum by counting (value desc, position asc); nb_total <= 1024
+    const float* b = bm + static_cast<size_t>(q) * nb_total;
+    float kth = -INFINITY, top = -INFINITY;
+    for (int i0 = 0; i0 < nb_total; i0 += 32) {
+        const int i = i0 + lane;
+        const float v = i < nb_total ? __ldg(b + i) : -INFINITY;
+        int rank = 0;
+        for (int j = 0; j < nb_total; ++j) {
+            const float w = __ldg(b + j);
+            rank += (w > v || (w == v && j < i)) ? 1 : 0;
+        }
+        if (i < nb_total && rank == m - 1) kth = v;
+        if (i < nb_total && rank == 0) top = v;
+    }
+    for (int o = 16; o; o >>= 1) {
+        kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+        top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
+    }
+    if (lane == 0 && kth > -INFINITY) atomicMax(thr_enc + q, enc_score(kth));
+    if (!hq) return;
     double qq = 0.0;
     for (int c = lane; c < dim; c += 32) {
         const double v = static_cast<double>(__ldg(queries + static_cast<size_t>(q) * dim + c));
         qq += v * v;
     }
     for (int o = 16; o; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
-    for (int b = lane; b < kHistBuckets; b += 32) hist[static_cast<size_t>(q) * kHistBuckets + b] = 0u;
+    for (int c = lane; c < kHistBuckets; c += 32) hist[static_cast<size_t>(q) * kHistBuckets + c] = 0u;
     if (lane) return;
     const double eps = bf16_score_error_bound(sqrt(qq) * (1.0 + 1e-9), static_cast<double>(__ldg(max_half_sqnorm)), dim, metric);
-    const float lo = dec_score(thr_enc[q]), top = dec_score(top_enc[q]);
+    const float lo = kth;
     const float span = (top - lo) * (2.5f / kHistBuckets);
     float4 r;
     r.x = lo;
@@ -1026,7 +1071,7 @@ static PackedGallery gallery_layout(long long n_rows, int dim) {
 }
 
 struct SearchWs {
-    size_t q_bf16, thr, cand_n, cand_s, cand_i, prog, top, hq, hist, total;
+    size_t q_bf16, thr, cand_n, cand_s, cand_i, prog, bm, hq, hist, total;
     int kcap;
     SearchPlan plan;
 };
@@ -1050,7 +1095,7 @@ static SearchWs search_ws(long long n_rows, int dim, int n_query, int k) {
     w.cand_i = take(slots * w.kcap * 4);
     w.prog = take(static_cast<size_t>(w.plan.n_units) * 4);
     const size_t q_pad = static_cast<size_t>(w.plan.n_qgroups) * w.plan.cl * 128;
-    w.top = take(q_pad * 4);
+    w.bm = take(q_pad * kSeedSegments * 2 * w.kcap * 4);     // pooled block maxima of the seeding sweep
     w.hq = take(q_pad * 16);
     w.hist = take(q_pad * kHistBuckets * 4);
     w.total = o;
@@ -1104,7 +1149,7 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
     if (prof_on < 0) { const char* e = getenv("OFX_TC_PROF"); prof_on = (e && e[0] == '1') ? 1 : 0; }
     if (prof_on) {   // debug only: synchronous dump of per-CTA wait counters (tc_pipeline.cuh)
         if (!prof_dev) OFX_CUDA(cudaMalloc(&prof_dev, 8 * 8 * 256));
-        OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 256, stream));
+        OFX_CUDA(cudaMemsetAsync(prof_dev, 0, 8 * 8 * 256, stream));   // 2048 counters: 8 per CTA, timeline from 1199
         OFX_CUDA(cudaMemcpyToSymbolAsync(g_tc_prof, &prof_dev, sizeof(prof_dev), 0, cudaMemcpyHostToDevice, stream));
     }
 #else
@@ -1118,6 +1163,10 @@ static int launch_search(const void* q_bf16, int n_query, const void* gallery, l
         OFX_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
         fprintf(stderr, "search prof nq=%d rows=%lld grid=%d cl=%d seg_tiles=%d sub=%d: cta0 mma total %lld wait_full %lld wait_tmem_empty %lld | epi total %lld wait_tmem_full %lld ; cta100 mma %lld %lld %lld | epi %lld %lld\n",
                 n_query, n_rows, pl.grid, CL, pl.seg_tiles, pl.sub_tiles, h[0], h[1], h[2], h[4], h[5], h[800], h[801], h[802], h[804], h[805]);
+        // per-unit timeline of CTA 0's first epilogue warp: wall cycles, of which inside Epi::tile (busy includes the
+        // wait share measured separately = waiting for the accumulator)
+        for (int u = 0; u < h[1199] && u < 40; ++u)
+            fprintf(stderr, "  unit %2d: %9lld cycles, epilogue tile() %9lld, waiting for tmem_full %9lld\n", u, h[1200 + 3 * u], h[1201 + 3 * u], h[1202 + 3 * u]);
     }
     return OFX_OK;
 }
@@ -1225,7 +1274,7 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
         const long long warm_rows = kWarmRows * (W.kcap / 32);    // 2 kcap blocks of 128 rows by default
         static int use_hist = -1;       // OFX_SEARCH_HIST=0: no counting bound (A/B timing)
         if (use_hist < 0) { const char* e = getenv("OFX_SEARCH_HIST"); use_hist = (e && e[0] == '0') ? 0 : 1; }
-        uint32_t* top = reinterpret_cast<uint32_t*>(ws + W.top);
+        float* bm = reinterpret_cast<float*>(ws + W.bm);
         float4* hq = nullptr;
         uint32_t* hist = nullptr;
         if (kWarmRows > 0 && n_rows >= 16 * warm_rows) {
@@ -1236,31 +1285,41 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
                     OFX_TRY((launch_search_cl<EpiTopK<32>, 4, 6>(q_bf16, n_query, pk, kWarmRows, wp, ep, dim, st)));
                 }
             } else if (warm_rows / 128 >= W.kcap) {
-                SearchPlan wp = W.plan;             // same query blocks / cluster shape, ONE segment over the sample
-                wp.n_tiles = static_cast<int>(warm_rows / kSearchBN);
-                wp.n_seg = 1;
-                wp.seg_tiles = wp.n_tiles;
-                wp.n_units = wp.n_qgroups;
+                // same query blocks / cluster shape; one sample segment of warm_rows rows per idle CTA pair of a
+                // query group (all units run in one wave), at most kSeedSegments and 1/16 of the shard
+                SearchPlan wp = W.plan;
                 const int n_cl = sm_count() / wp.cl;
+                int n_seg = n_cl / (wp.n_qgroups > 0 ? wp.n_qgroups : 1);
+                n_seg = n_seg < 1 ? 1 : (n_seg > kSeedSegments ? kSeedSegments : n_seg);
+                while (n_seg > 1 && n_rows < 16 * warm_rows * n_seg) --n_seg;
+                static int seed_seg = -1;       // OFX_SEED_SEGMENTS: cap (A/B timing)
+                if (seed_seg < 0) { const char* e = getenv("OFX_SEED_SEGMENTS"); seed_seg = e ? atoi(e) : kSeedSegments; }
+                if (seed_seg >= 1 && n_seg > seed_seg) n_seg = seed_seg;
+                const long long sample_rows = warm_rows * n_seg;
+                wp.seg_tiles = static_cast<int>(warm_rows / kSearchBN);
+                wp.n_seg = n_seg;
+                wp.n_tiles = wp.seg_tiles * n_seg;
+                wp.n_units = wp.n_qgroups * n_seg;
                 wp.grid = (wp.n_units < n_cl ? wp.n_units : n_cl) * wp.cl;
+                const int nb_seg = static_cast<int>(warm_rows / 128), nb_total = nb_seg * n_seg;
                 if (W.kcap == 32) {
-                    EpiBlockMax<64>::Params ep{warm_rows, n_query, thr, 32, prog, top};
-                    OFX_TRY((launch_search_cl<EpiBlockMax<64>, 4, 6>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
+                    EpiBlockMax<64>::Params ep{sample_rows, n_query, prog, bm, nb_seg, nb_total};
+                    OFX_TRY((launch_search_cl<EpiBlockMax<64>, 4, 6>(q_bf16, n_query, pk, sample_rows, wp, ep, dim, st)));
                 } else if (W.kcap == 64) {
-                    EpiBlockMax<128>::Params ep{warm_rows, n_query, thr, 64, prog, top};
-                    OFX_TRY((launch_search_cl<EpiBlockMax<128>, 3, 5>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
+                    EpiBlockMax<128>::Params ep{sample_rows, n_query, prog, bm, nb_seg, nb_total};
+                    OFX_TRY((launch_search_cl<EpiBlockMax<128>, 3, 5>(q_bf16, n_query, pk, sample_rows, wp, ep, dim, st)));
                 } else {
-                    EpiBlockMax<256>::Params ep{warm_rows, n_query, thr, 128, prog, top};
-                    OFX_TRY((launch_search_cl<EpiBlockMax<256>, 2, 3>(q_bf16, n_query, pk, warm_rows, wp, ep, dim, st)));
+                    EpiBlockMax<256>::Params ep{sample_rows, n_query, prog, bm, nb_seg, nb_total};
+                    OFX_TRY((launch_search_cl<EpiBlockMax<256>, 2, 3>(q_bf16, n_query, pk, sample_rows, wp, ep, dim, st)));
                 }
-                if (use_hist) {       // every query has a seeded bound and a sample maximum: the counting bound can run
+                if (use_hist) {       // every query gets a seeded bound and a sample maximum: the counting bound can run
                     hq = reinterpret_cast<float4*>(ws + W.hq);
                     hist = reinterpret_cast<uint32_t*>(ws + W.hist);
-                    hist_setup_kernel<<<(n_query + 7) / 8, 256, 0, st>>>(queries, n_query, dim, metric, thr, top,
-                        reinterpret_cast<const float*>(pk + L.stats), hq, hist);
-                    OFX_LAUNCH_CHECK();
-                    count_launch();
                 }
+                seed_finish_kernel<<<(n_query + 7) / 8, 256, 0, st>>>(queries, n_query, dim, metric, bm, nb_total, W.kcap, thr,
+                    reinterpret_cast<const float*>(pk + L.stats), hq, hist);
+                OFX_LAUNCH_CHECK();
+                count_launch();
             }
         }
         if (W.kcap == 32) {

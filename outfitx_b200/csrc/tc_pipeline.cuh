@@ -237,13 +237,34 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
         epi.begin(ep, sched, ewarp, lane, epi_smem);
         long long* prof = g_tc_prof;
         long long t0 = clock64(), t_tf = 0, tq;
+#ifdef OFX_DEBUG
+        long long tl_start = t0, tl_busy = 0, tl_wait0 = 0;    // per-unit timeline of CTA 0 (search schedules only)
+        int tl_n = 0;
+#endif
         while (sched.next()) {
+#ifdef OFX_DEBUG
+            if constexpr (Sched::kPrefetch) {
+                if (prof && blockIdx.x == 0 && ewarp == 0 && lane == 0 && sched.first && sched.it == 0) {
+                    const long long now = clock64();
+                    if (tl_n > 0 && tl_n <= 40) {
+                        prof[1200 + 3 * (tl_n - 1)] = now - tl_start;
+                        prof[1200 + 3 * (tl_n - 1) + 1] = tl_busy;
+                        prof[1200 + 3 * (tl_n - 1) + 2] = t_tf - tl_wait0;
+                    }
+                    tl_start = now; tl_busy = 0; tl_wait0 = t_tf; ++tl_n;
+                }
+            }
+            const long long tl_t = clock64();
+#endif
             epi.pre_tile(ep, sched, ewarp, lane, epi_smem);   // e.g. start fetching the residual tile
             if (prof) { tq = clock64(); mbar_wait(&tmem_full[acc], acc_phase); t_tf += clock64() - tq; }
             else mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
             epi.tile(ep, sched, t_acc, ewarp, lane, epi_smem);
+#ifdef OFX_DEBUG
+            tl_busy += clock64() - tl_t;
+#endif
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -253,6 +274,16 @@ tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         epi.end(ep, lane);
+#ifdef OFX_DEBUG
+        if constexpr (Sched::kPrefetch) {
+            if (prof && blockIdx.x == 0 && ewarp == 0 && lane == 0 && tl_n > 0 && tl_n <= 40) {
+                prof[1200 + 3 * (tl_n - 1)] = clock64() - tl_start;
+                prof[1200 + 3 * (tl_n - 1) + 1] = tl_busy;
+                prof[1200 + 3 * (tl_n - 1) + 2] = t_tf - tl_wait0;
+                prof[1199] = tl_n;
+            }
+        }
+#endif
         if (prof && ewarp == 0 && lane == 0) {
             prof[blockIdx.x * 8 + 4] = clock64() - t0; prof[blockIdx.x * 8 + 5] = t_tf;
         }
