@@ -35,7 +35,8 @@ for f in sorted(os.listdir(src)):
                     "dram_bytes": dram(d), "kernel": d["Kernel Name"][0][:80],
                     "us": float(d["gpu__time_duration.sum"][0].replace(",", "")) * {"ms": 1e3, "us": 1, "ns": 1e-3, "s": 1e6}[d["gpu__time_duration.sum"][1]],
                     "source": f"ncu --set full --clock-control none of tools/prof_step.py --skip-cp --rows {m.group(1)} "
-                              f"(8192 queries, top-10), summary in profiles/r2_ncu_search_{m.group(1)}.txt"}
+                              f"({4096 if m.group(1) == '1000000' else 8192} queries, top-10), summary in "
+                              f"profiles/r2_ncu_search_{m.group(1)}.txt"}
 lc = os.path.join(src, "launches_cp.csv")
 if os.path.exists(lc):
     lines = [l for l in open(lc) if not l.startswith("==")]

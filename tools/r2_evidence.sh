@@ -8,10 +8,10 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__data_
 python tools/prof_step.py --skip-cir > $O/cp_plain.log 2>&1 && \
 ncu --metrics $M --clock-control none -c 400 --csv --log-file $O/launches_cp.csv python tools/prof_step.py --skip-cir > $O/cp_ncu.log 2>&1
 echo "cp launches rc $?"
-for R in 1250000 10000000; do
-  python tools/prof_step.py --skip-cp --rows $R > $O/search_plain_$R.log 2>&1 && \
-  ncu --metrics $M --clock-control none -c 60 --csv --log-file $O/launches_search_$R.csv python tools/prof_step.py --skip-cp --rows $R > $O/search_ncu_l_$R.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k 'regex:tc_kernel|merge_rerank|topk_merge' --launch-skip 6 -c 3 -o $O/search_$R -f python tools/prof_step.py --skip-cp --rows $R > $O/search_ncu_f_$R.log 2>&1
+for R in 1250000 10000000 1000000; do
+  python tools/prof_step.py --skip-cp --rows $R $( [ $R = 1000000 ] && echo --queries 4096 ) > $O/search_plain_$R.log 2>&1 && \
+  ncu --metrics $M --clock-control none -c 60 --csv --log-file $O/launches_search_$R.csv python tools/prof_step.py --skip-cp --rows $R $( [ $R = 1000000 ] && echo --queries 4096 ) > $O/search_ncu_l_$R.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k 'regex:tc_kernel|merge_rerank|topk_merge' --launch-skip 6 -c 3 -o $O/search_$R -f python tools/prof_step.py --skip-cp --rows $R $( [ $R = 1000000 ] && echo --queries 4096 ) > $O/search_ncu_f_$R.log 2>&1
   echo "search $R rc $?"
 done
 python tools/time_ffn.py 82158 > $O/ffn_plain.log 2>&1 && \
