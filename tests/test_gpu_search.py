@@ -254,3 +254,32 @@ def test_certificate_on_ordinary_data():
     for k in (10, 50):
         _, _, proved = local_search(_t(q), G, k, "l2", True, return_certified=True)
         assert bool(proved.all())
+
+
+@pytest.mark.parametrize("case", ["flat_sample", "outlier_in_sample", "negative_dot", "few_queries_k50"])
+def test_counting_bound_on_awkward_samples(case):
+    """The seeded bound and the counting histogram are derived from the FIRST rows of the shard (up to four sample
+    segments of pooled block maxima).  Samples that say nothing about the rest -- all rows identical (zero bucket
+    width), one huge outlier (one bucket holds everything), all scores negative (dot metric) -- must only cost
+    speed: indices stay those of the fp64 oracle and the scores stay exact."""
+    from outfitx_b200.search import Gallery, local_search
+    n, k, metric, nq = 560_000, 10, "l2", 40
+    gal = synth.make_items(n, 512, seed=77)
+    q = synth.make_queries(nq, 1024, seed=78) * np.float32(0.05)
+    if case == "flat_sample":
+        gal[:40_000] = gal[0]
+    elif case == "outlier_in_sample":
+        gal[1234] *= np.float32(40.0)
+        q[:4] = gal[1234] * np.float32(0.02) + q[:4]
+    elif case == "negative_dot":
+        metric = "dot"
+        gal = -np.abs(gal)
+        q = np.abs(q)
+    elif case == "few_queries_k50":
+        k, nq = 50, 3
+        q = q[:3]
+    G = Gallery.build(_t(gal))
+    idx, score, proved = local_search(_t(q), G, k, metric, True, return_certified=True)
+    want_i, want_s = R.search(q, gal, k=k, metric=metric)
+    assert np.array_equal(idx.cpu().numpy(), want_i)
+    np.testing.assert_allclose(score.cpu().numpy(), want_s, rtol=1e-13, atol=1e-11)
