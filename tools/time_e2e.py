@@ -16,7 +16,7 @@ def t(fn, n=10):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(n): fn()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
-for chunk, tail in ((2048, 2048), (2048, 1024), (2048, 512), (1536, 1536), (1536, 768), (3072, 1024), (2560, 2560)):
+for chunk, tail in ((2048, 2048), (2048, 1024), (1536, 1536), (2731, 2731), (2560, 2560)):
     pipe = HostScoringPipeline(model, chunk=chunk); pipe.tail_min = tail
     b = t(lambda: pipe.score_packed(ir, tr, lens, host["text"], host["cand"]))
     print(f"chunk {chunk} tail_min {tail}: plan {[hi - lo for lo, hi in pipe._plan(B, True)]}  packed {b:.2f} ms ({B/b*1e3:,.0f}/s)", flush=True)
@@ -34,8 +34,3 @@ t0 = time.perf_counter()
 for _ in range(20):
     lens64 = lens.to(torch.int64); off = torch.zeros(B + 1, dtype=torch.int64); torch.cumsum(lens64, 0, out=off[1:])
 print(f"host-side collate arithmetic: {(time.perf_counter()-t0)/20*1e3:.3f} ms")
-import cProfile, pstats
-pipe = HostScoringPipeline(model, chunk=2048)
-pr = cProfile.Profile(); pr.enable()
-for _ in range(5): pipe.score_packed(ir, tr, lens, host["text"], host["cand"])
-pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
