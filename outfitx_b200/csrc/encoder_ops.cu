@@ -354,7 +354,6 @@ template int cast_rows<__nv_bfloat16>(const float*, long long, __nv_bfloat16*, c
 template <int HD, class T>
 __global__ void __launch_bounds__(256)
 attention_kernel(AttnArgs a) {
-    constexpr int kMaxS = 17;
     constexpr int NP = HD / 32;  // 8-dim pieces per lane
     const int n_rows = a.row0_only ? a.batch : min(*a.n_tok, a.max_rows);
     const int row = blockIdx.x * 4 + (threadIdx.x >> 6);

@@ -190,8 +190,6 @@ ffn_block2_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_consta
     const int nch = p.nch;
     int* my_uflag = p.uflag + ((group * 2 + side) * 2 + rank) * NSLOT;              // what THIS CTA's epilogue publishes
     const int* peer_uflag = p.uflag + ((group * 2 + (side ^ 1)) * 2 + rank) * NSLOT; // what the partner's same-rank CTA publishes
-    int* my_uack = p.uack + group * 2 + side;                              // partner's acks of OUR chunks
-    int* peer_uack = p.uack + group * 2 + (side ^ 1);                      // our acks of the PARTNER's chunks
     int* xflag = p.xflag + (group * 2 + rank) * 2;                         // [side]: the rows' two column halves
     // scratch rows: ((((group * 2 + side) * 2 + rank) * NSLOT + slot) * 128 + row), 128 hidden columns each
     const int my_srow = ((group * 2 + side) * 2 + static_cast<int>(rank)) * NSLOT * ROWS;
