@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the outfit-scoring hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--skip cir,cir3,large]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--skip cir,cir3,large,fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on rank 0.  Primary metric: CP outfits/s on BASELINE.json configs[1]
@@ -14,6 +14,7 @@ collective).  The same line carries one object per remaining config, each with i
   cir3   configs[2] (N = 1 only): 4096 ENCODER-PRODUCED queries (d_model 1024 CIR forward) + exact top-10 over
          1 M items, embed + search timed together.
   large  configs[4] (N = 1 only): large-encoder CP sweep, d_model 1024, 16 items, batch 256 .. 32768.
+  fp32   (N = 1 only) the headline step with precision="fp32": linear layers as bf16 hi / lo split GEMMs on tcgen05.
 
 `--impl reference` times the reference's CPU path (oracle/torch_port.py: the stock torch modules the
 reference itself is built from -- the reference is pure Python and cannot travel to the GPU box) on the host
@@ -216,11 +217,11 @@ def make_cp_inputs(batch, dev, seed):
     return img, txt, mask, text, cand, lengths
 
 
-def make_model(dev, d_model=D_MODEL):
+def make_model(dev, d_model=D_MODEL, precision="bf16"):
     import outfitx_b200 as o
     method = "mean" if d_model == 512 else "concat"
     cfg = o.OutfitXConfig(item_encoder=o.ItemEncoderConfig(type="clip", aggregation_method=method))
-    m = o.OutfitX(cfg, precision="bf16")
+    m = o.OutfitX(cfg, precision=precision)
     sd = synth.make_state_dict(d_model, D_EMBED, seed=0)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     return m.to(dev), sd
@@ -489,7 +490,7 @@ def main():
     ap.add_argument("--cir-rows", type=int, default=10_000_000)
     ap.add_argument("--cir-queries", type=int, default=8192)
     ap.add_argument("--cir-steps", type=int, default=0, help="0 = min(steps, 5)")
-    ap.add_argument("--skip", default="", help="comma list of cir, cir3, large, cpu")
+    ap.add_argument("--skip", default="", help="comma list of cir, cir3, large, fp32, cpu")
     ap.add_argument("--no-cir", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=512)
@@ -617,6 +618,31 @@ def main():
         vhow = (f"first {n} outfits vs the CPU port: max |prob - ref| = {dprob:.2e} (bar 2e-2); FITB argmin equal on "
                 f"{float(agree.float().mean()):.4f} of them, every difference a near-tie (gap of the two best reference "
                 f"distances < 2e-2: {near}); packed-layout e2e results bit-identical to the device-resident ones: {packed_same}")
+    # the same step in precision="fp32": every nn.Linear on the tensor cores as a bf16 hi / lo split GEMM (N = 1 only)
+    fp32 = None
+    if world == 1 and "fp32" not in skip:
+        m32, _ = make_model(dev, precision="fp32")
+        st32 = {}
+
+        def fp32_step():
+            st32["probs"] = m32.score_cp(outfit_mask=mask, encoder_input_dict=enc)
+            st32["fitb"] = m32.score_fitb(outfit_mask=mask, target_item_text_embedding=text,
+                                          candidate_item_embedding=cand, encoder_input_dict=enc)
+
+        k32 = max(2, min(args.steps, 3))
+        ms32 = timed(fp32_step, k32, 3, False, dev) / k32
+        fp32 = {"metric": "CP outfits/sec, precision=fp32", "value": B / (ms32 * 1e-3), "unit": "outfits/s", "ms_per_step": ms32,
+                "dtype": "f32 operands as bf16 hi + lo pieces on tcgen05 (3 products, fp32 accumulation); attention, LayerNorm, "
+                         "heads in fp32 on the CUDA cores",
+                "config": {"workload": "configs[1] (CP + FITB, 8192 outfits) with precision='fp32'"}}
+        if cpu is not None:
+            n = min(args.cpu_sample, B)
+            dp = float((st32["probs"][:n].cpu() - want_p).abs().max())
+            same = bool((st32["fitb"][0][:n].cpu() == want_pred).all())
+            fp32["verified"] = bool(dp <= 1e-4 and same)
+            fp32["verified_how"] = (f"first {n} outfits vs the CPU port (fp32): max |prob - ref| = {dp:.2e} (bar 1e-4), "
+                                    f"FITB argmin identical: {same}")
+        del m32, st32
     del host, img_rows, txt_rows
     torch.cuda.empty_cache()
 
@@ -718,7 +744,7 @@ def main():
             "gpu_launches": int(launches_cp),
             "cpu_baseline": cpu,
             "verified": verified, "verified_how": vhow,
-            "cir": cir, "cir3": cir3, "large": large,
+            "cir": cir, "cir3": cir3, "large": large, "fp32": fp32,
         }
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if dist_ok:

@@ -233,6 +233,16 @@ OFX_API int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw
                   int32_t k, const float* bias, int32_t act_mish, const float* residual,
                   int64_t ldr, void* out, int64_t ldo, int32_t out_f32, void* stream);
 
+/* ---- the fp32 mode's linear layer on the tensor cores: fp32 A (M,K) and W (N,K) are cut into bf16 hi / lo pieces
+ * (16 mantissa bits) and  A.W^T ~= A_hi.W_hi^T + A_lo.W_hi^T + A_hi.W_lo^T  runs as ONE bf16 tcgen05 GEMM with K' = 3K
+ * and fp32 accumulation (relative error ~2^-16 instead of bf16's 2^-8); out fp32.  What precision="fp32" of
+ * ofx_encoder_forward uses for every nn.Linear (weights are split once by ofx_pack_weights).  K % 64 == 0,
+ * N % 128 == 0.  workspace: ofx_gemm_f32_tc_workspace_bytes(m, n, k) bytes, 256-byte aligned. */
+OFX_API size_t ofx_gemm_f32_tc_workspace_bytes(int32_t m, int32_t n, int32_t k);
+OFX_API int ofx_gemm_f32_tc(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t m, int32_t n, int32_t k,
+                    const float* bias, int32_t act_mish, const float* residual, int64_t ldr, float* out,
+                    int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- building block exported for tests / profiling: the fused feed-forward block of one
  * encoder layer,  x <- x + W2 . mish(W1 . LayerNorm(x) + b1) + b2  in place on the fp32 rows
  * (torch TransformerEncoderLayer._ff_block as configured at outfit_x.py:32-45).

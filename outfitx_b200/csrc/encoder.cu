@@ -17,6 +17,9 @@ struct WLayout {
     size_t esz;
     size_t w_qkv, w_o, w_1, w_2, b_qkv, b_o, b_1, b_2, ln1w, ln1b, ln2w, ln2b, layer_bytes;
     size_t g_token, g_timg, g_cpw, g_cpb, g_cir, total;
+    // fp32 precision only: the GEMM weights once more as bf16 hi / lo pieces [hi | hi | lo] along K (gemm.h), so that
+    // the fp32 mode's linear layers run on the tensor cores (0 = absent)
+    size_t s_qkv, s_o, s_1, s_2, s_cir;
 };
 
 static int check_shape(const ofx_shape* s) {
@@ -49,6 +52,12 @@ static WLayout make_layout(const ofx_shape* s) {
     L.b_1 = take(fp * 4);
     L.b_2 = take(dm * 4);
     L.ln1w = take(dm * 4); L.ln1b = take(dm * 4); L.ln2w = take(dm * 4); L.ln2b = take(dm * 4);
+    if (s->precision == OFX_PREC_FP32) {
+        L.s_qkv = take(3 * dm * 3 * dm * 2);
+        L.s_o = take(dm * 3 * dm * 2);
+        L.s_1 = take(fp * 3 * dm * 2);
+        L.s_2 = take(dm * 3 * fp * 2);
+    }
     L.layer_bytes = o;
     o = L.layer_bytes * L.nl;
     L.g_token = take(dm * 4);
@@ -56,6 +65,7 @@ static WLayout make_layout(const ofx_shape* s) {
     L.g_cpw = take(dm * 4);
     L.g_cpb = take(256);
     L.g_cir = take(static_cast<size_t>(L.de) * dm * L.esz);
+    if (s->precision == OFX_PREC_FP32) L.s_cir = take(static_cast<size_t>(L.de) * 3 * dm * 2);
     L.total = o;
     return L;
 }
@@ -80,6 +90,13 @@ static int pack_all(const WLayout& L, const float* const* p, uint8_t* dst, cudaS
         OFX_TRY(pack_matrix<float>(q[OFX_W_NORM1_B], 1, L.dm, reinterpret_cast<float*>(base + L.ln1b), 1, L.dm, st));
         OFX_TRY(pack_matrix<float>(q[OFX_W_NORM2_W], 1, L.dm, reinterpret_cast<float*>(base + L.ln2w), 1, L.dm, st));
         OFX_TRY(pack_matrix<float>(q[OFX_W_NORM2_B], 1, L.dm, reinterpret_cast<float*>(base + L.ln2b), 1, L.dm, st));
+        if (sizeof(T) == 4 && L.s_qkv) {     // the packed (padded) fp32 matrices -> bf16 hi / lo pieces
+            auto f = [&](size_t o) { return reinterpret_cast<const float*>(base + o); };
+            OFX_TRY(split_bf16x3(f(L.w_qkv), L.dm, 3 * L.dm, nullptr, L.dm, base + L.s_qkv, kSplitW, st));
+            OFX_TRY(split_bf16x3(f(L.w_o), L.dm, L.dm, nullptr, L.dm, base + L.s_o, kSplitW, st));
+            OFX_TRY(split_bf16x3(f(L.w_1), L.dm, L.fp, nullptr, L.dm, base + L.s_1, kSplitW, st));
+            OFX_TRY(split_bf16x3(f(L.w_2), L.fp, L.dm, nullptr, L.fp, base + L.s_2, kSplitW, st));
+        }
     }
     const float* const* g = p + L.nl * OFX_W_PER_LAYER;
     for (int i = 0; i < OFX_W_GLOBAL; ++i)
@@ -89,12 +106,14 @@ static int pack_all(const WLayout& L, const float* const* p, uint8_t* dst, cudaS
     OFX_TRY(pack_matrix<float>(g[OFX_G_CP_W], 1, L.dm, reinterpret_cast<float*>(dst + L.g_cpw), 1, L.dm, st));
     OFX_TRY(pack_matrix<float>(g[OFX_G_CP_B], 1, 1, reinterpret_cast<float*>(dst + L.g_cpb), 1, 1, st));
     OFX_TRY(pack_matrix<T>(g[OFX_G_CIR_W], L.de, L.dm, reinterpret_cast<T*>(dst + L.g_cir), L.de, L.dm, st));
+    if (sizeof(T) == 4 && L.s_cir)
+        OFX_TRY(split_bf16x3(reinterpret_cast<const float*>(dst + L.g_cir), L.dm, L.de, nullptr, L.dm, dst + L.s_cir, kSplitW, st));
     return OFX_OK;
 }
 
 // workspace carve-up (all 256-byte aligned)
 struct WsLayout {
-    size_t off, n_tok, owner, x, h, big, q0, a0, u0, ffn, ffn_bytes, total;
+    size_t off, n_tok, owner, x, h, big, q0, a0, u0, ffn, ffn_bytes, split, total;
     int t_max, big_ld;
 };
 static WsLayout make_ws(const ofx_shape* s, int batch) {
@@ -118,6 +137,8 @@ static WsLayout make_ws(const ofx_shape* s, int batch) {
     // the fused FFN block's exchange ring + counters (bf16 path, d_model 512)
     W.ffn_bytes = (s->precision == OFX_PREC_BF16 && ffn_block_supported(s->d_model, static_cast<int>(fp))) ? ffn_block_workspace_bytes() : 0;
     W.ffn = take(W.ffn_bytes);
+    // fp32 precision: bf16 hi / lo pieces of the current GEMM's activation operand (3 x K bf16 per token row)
+    W.split = take(s->precision == OFX_PREC_FP32 ? t * 3 * (dm > fp ? dm : fp) * 2 : 0);
     W.total = o;
     return W;
 }
@@ -137,6 +158,16 @@ static bool ffn_emits_ln() {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("OFX_FFN_LN");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+// OFX_FP32_TC=0: the fp32 mode's linear layers on the CUDA cores (gemm_f32) instead of the split-bf16 tensor-core form
+static bool fp32_tc_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("OFX_FP32_TC");
         on = (e && e[0] == '0') ? 0 : 1;
     }
     return on == 1;
@@ -163,6 +194,22 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
     T* u0 = reinterpret_cast<T*>(ws + W.u0);
     auto lw = [&](int l, size_t o) { return wts + L.layer_bytes * l + o; };
     auto lf = [&](int l, size_t o) { return reinterpret_cast<const float*>(lw(l, o)); };
+    // linear layer: bf16 mode -> tcgen05 GEMM on the bf16 operands; fp32 mode -> the activation operand is cut into
+    // bf16 hi / lo pieces and multiplied with the pre-split weights on the same tensor-core pipeline (gemm.h)
+    uint8_t* split_a = ws + W.split;
+    const bool tc32 = sizeof(T) == 4 && L.s_qkv && fp32_tc_enabled();
+    auto mm = [&](const GemmArgs& g, const uint8_t* w_split) -> int {
+        if constexpr (sizeof(T) == 4) {
+            if (tc32) {
+                OFX_TRY(split_bf16x3(static_cast<const float*>(g.a), g.lda, g.m, g.m_dev, g.k, split_a, kSplitA, st));
+                GemmArgs t = g;
+                t.a = split_a; t.lda = 3LL * g.k; t.w = w_split; t.ldw = 3LL * g.k; t.out_f32 = 1;
+                return gemm_f32_split(t, st);
+            }
+        }
+        (void)w_split;
+        return gemm<T>(g, st);
+    };
     const bool fused_ffn = sizeof(T) == 2 && ffn_block_supported(dm, fp) && fused_ffn_enabled();
 
     OFX_TRY(scan_valid(a->mask, B, s->max_items, off, n_tok, st));
@@ -191,13 +238,13 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
         if (!last) {
             // dense layer over every valid token
             GemmArgs g{h, dm, lw(l, L.w_qkv), dm, W.t_max, n_tok, 3 * dm, dm, lf(l, L.b_qkv), 0, nullptr, 0, big, 3 * dm, 0};
-            OFX_TRY(gemm<T>(g, st));
+            OFX_TRY(mm(g, lw(l, L.s_qkv)));
             at.row0_only = 0;
             at.q = big; at.k = big + dm; at.v = big + 2 * dm; at.ldq = at.ldk = at.ldv = 3 * dm;
             at.out = h; at.ldo = dm;
             OFX_TRY(attention<T>(at, hd, st));
             GemmArgs go{h, dm, lw(l, L.w_o), dm, W.t_max, n_tok, dm, dm, lf(l, L.b_o), 0, x, dm, x, dm, 1};
-            OFX_TRY(gemm<T>(go, st));
+            OFX_TRY(mm(go, lw(l, L.s_o)));
             if (fused_ffn) {
                 FfnBlockArgs fa{x, W.t_max, n_tok, dm, fp, lf(l, L.ln2w), lf(l, L.ln2b), lw(l, L.w_1),
                                 lf(l, L.b_1), lw(l, L.w_2), lf(l, L.b_2)};
@@ -207,24 +254,24 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
             } else {
                 OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
                 GemmArgs g1{h, dm, lw(l, L.w_1), dm, W.t_max, n_tok, fp, dm, lf(l, L.b_1), 1, nullptr, 0, big, fp, 0};
-                OFX_TRY(gemm<T>(g1, st));
+                OFX_TRY(mm(g1, lw(l, L.s_1)));
                 GemmArgs g2{big, fp, lw(l, L.w_2), fp, W.t_max, n_tok, dm, fp, lf(l, L.b_2), 0, x, dm, x, dm, 1};
-                OFX_TRY(gemm<T>(g2, st));
+                OFX_TRY(mm(g2, lw(l, L.s_2)));
             }
         } else {
             // last layer: K,V for every token, everything else for the prefix row only
             const T* w_in = reinterpret_cast<const T*>(lw(l, L.w_qkv));
             GemmArgs gkv{h, dm, w_in + static_cast<size_t>(dm) * dm, dm, W.t_max, n_tok, 2 * dm, dm,
                          lf(l, L.b_qkv) + dm, 0, nullptr, 0, big, 2 * dm, 0};
-            OFX_TRY(gemm<T>(gkv, st));
+            OFX_TRY(mm(gkv, lw(l, L.s_qkv) + static_cast<size_t>(dm) * 3 * dm * 2));     // rows dm.. of the split W_qkv
             GemmArgs gq{h, dm, w_in, dm, B, nullptr, dm, dm, lf(l, L.b_qkv), 0, nullptr, 0, q0, dm, 0};
-            OFX_TRY(gemm<T>(gq, st));
+            OFX_TRY(mm(gq, lw(l, L.s_qkv)));
             at.row0_only = 1;
             at.q = q0; at.ldq = dm; at.k = big; at.v = big + dm; at.ldk = at.ldv = 2 * dm;
             at.out = a0; at.ldo = dm;
             OFX_TRY(attention<T>(at, hd, st));
             GemmArgs go{a0, dm, lw(l, L.w_o), dm, B, nullptr, dm, dm, lf(l, L.b_o), 0, x, dm, x, dm, 1};
-            OFX_TRY(gemm<T>(go, st));
+            OFX_TRY(mm(go, lw(l, L.s_o)));
             if (fused_ffn) {
                 FfnBlockArgs fa{x, B, nullptr, dm, fp, lf(l, L.ln2w), lf(l, L.ln2b), lw(l, L.w_1),
                                 lf(l, L.b_1), lw(l, L.w_2), lf(l, L.b_2)};
@@ -233,9 +280,9 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
             } else {
                 OFX_TRY(layernorm<T>(x, B, nullptr, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
                 GemmArgs g1{h, dm, lw(l, L.w_1), dm, B, nullptr, fp, dm, lf(l, L.b_1), 1, nullptr, 0, u0, fp, 0};
-                OFX_TRY(gemm<T>(g1, st));
+                OFX_TRY(mm(g1, lw(l, L.s_1)));
                 GemmArgs g2{u0, fp, lw(l, L.w_2), fp, B, nullptr, dm, fp, lf(l, L.b_2), 0, x, dm, x, dm, 1};
-                OFX_TRY(gemm<T>(g2, st));
+                OFX_TRY(mm(g2, lw(l, L.s_2)));
             }
         }
     }
@@ -245,7 +292,7 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
     } else {
         OFX_TRY(cast_rows<T>(x, static_cast<long long>(B) * dm, q0, st));
         GemmArgs gc{q0, dm, wts + L.g_cir, dm, B, nullptr, L.de, dm, nullptr, 0, nullptr, 0, a->query, L.de, 1};
-        OFX_TRY(gemm<T>(gc, st));
+        OFX_TRY(mm(gc, wts + L.s_cir));
         if (a->cand)
             OFX_TRY(fitb(a->query, a->cand, a->cand_ids, a->n_cand_rows, B, a->n_cand, L.de, a->fitb_dist,
                          reinterpret_cast<long long*>(a->fitb_argmin), st));
@@ -336,6 +383,29 @@ int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, int32_
     OFX_TRY(require_sm100());
     GemmArgs g{a, lda, w, ldw, m, nullptr, n, k, bias, act_mish, residual, ldr, out, ldo, out_f32};
     return gemm_bf16(g, static_cast<cudaStream_t>(stream));
+}
+
+size_t ofx_gemm_f32_tc_workspace_bytes(int32_t m, int32_t n, int32_t k) {
+    if (m < 0 || n <= 0 || k <= 0) return 0;
+    return align_up(static_cast<size_t>(m) * 3 * k * 2, 256) + align_up(static_cast<size_t>(n) * 3 * k * 2, 256);
+}
+
+int ofx_gemm_f32_tc(const float* a, int64_t lda, const float* w, int64_t ldw, int32_t m, int32_t n, int32_t k,
+                    const float* bias, int32_t act_mish, const float* residual, int64_t ldr, float* out,
+                    int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!a || !w || !out) return fail(OFX_E_ARG, "ofx_gemm_f32_tc: null operand");
+    if (m < 0 || n <= 0 || k <= 0) return fail(OFX_E_SHAPE, "ofx_gemm_f32_tc: M=%d N=%d K=%d", m, n, k);
+    const size_t need = ofx_gemm_f32_tc_workspace_bytes(m, n, k);
+    if (!workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace) % 256)
+        return fail(OFX_E_WORKSPACE, "ofx_gemm_f32_tc: workspace %zu B < required %zu B (256-byte aligned)", workspace_bytes, need);
+    OFX_TRY(require_sm100());
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* sa = static_cast<uint8_t*>(workspace);
+    uint8_t* sw = sa + align_up(static_cast<size_t>(m) * 3 * k * 2, 256);
+    OFX_TRY(split_bf16x3(a, lda, m, nullptr, k, sa, kSplitA, st));
+    OFX_TRY(split_bf16x3(w, ldw, n, nullptr, k, sw, kSplitW, st));
+    GemmArgs g{sa, 3LL * k, sw, 3LL * k, m, nullptr, n, k, bias, act_mish, residual, ldr, out, ldo, 1};
+    return gemm_f32_split(g, st);
 }
 
 size_t ofx_ffn_block_workspace_bytes(int32_t rows, int32_t d_model, int32_t d_ffn_padded) {

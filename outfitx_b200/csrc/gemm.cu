@@ -440,6 +440,51 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
 }
 
 // -------------------------------------------------------------------------------------
+// fp32 operands as bf16 hi / lo pieces (gemm.h): one thread per 4 consecutive K elements
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ src, long long ld, int rows, const int* __restrict__ rows_dev, int k,
+              __nv_bfloat16* __restrict__ dst, int order) {
+    const int n = rows_dev ? min(*rows_dev, rows) : rows;
+    const int k4 = k / 4;
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= static_cast<long long>(n) * k4) return;
+    const int r = static_cast<int>(i / k4), c = static_cast<int>(i - static_cast<long long>(r) * k4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * ld + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hi[j] = __float2bfloat16_rn(f[j]);
+        lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
+    }
+    __nv_bfloat16* o = dst + static_cast<long long>(r) * 3 * k + c;
+    const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(o) = h2;
+    *reinterpret_cast<uint2*>(o + k) = order == kSplitA ? l2 : h2;
+    *reinterpret_cast<uint2*>(o + 2 * k) = order == kSplitA ? h2 : l2;
+}
+
+int split_bf16x3(const float* src, long long ld, int rows, const int* rows_dev, int k, void* dst, int order,
+                 cudaStream_t stream) {
+    if (rows <= 0) return OFX_OK;
+    if (k % 4 || ld % 4 || (reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15)
+        return fail(OFX_E_ARG, "split_bf16x3: K and the pitch must be multiples of 4, pointers 16-byte aligned");
+    const long long n = static_cast<long long>(rows) * (k / 4);
+    split3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, ld, rows, rows_dev, k,
+                                                                              static_cast<__nv_bfloat16*>(dst), order);
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
+int gemm_f32_split(const GemmArgs& g, cudaStream_t stream) {
+    if (!g.out_f32) return fail(OFX_E_ARG, "gemm_f32_split: the output must be fp32");
+    GemmArgs t = g;
+    t.k = 3 * g.k;
+    return gemm_bf16(t, stream);
+}
+
+// -------------------------------------------------------------------------------------
 // fp32 CUDA-core path: 64x64 tile, 16-deep K slices, 4x4 outputs per thread
 // -------------------------------------------------------------------------------------
 constexpr int kFT = 64, kFK = 16;

@@ -24,4 +24,14 @@ struct GemmArgs {
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 int gemm_f32(const GemmArgs& g, cudaStream_t stream);
 
+// fp32 operands on the tensor cores: every fp32 value v is carried as two bf16 pieces hi = bf16(v), lo = bf16(v - hi)
+// (16 mantissa bits), laid out along K as three blocks so that an ordinary bf16 GEMM with K' = 3K evaluates
+//     A.W^T ~= A_hi.W_hi^T + A_lo.W_hi^T + A_hi.W_lo^T          (error ~2^-16 |a||w| per product, fp32 accumulation)
+// activations: [hi | lo | hi] (kSplitA), weights: [hi | hi | lo] (kSplitW).  rows_dev: optional device-side row count.
+constexpr int kSplitA = 0, kSplitW = 1;
+int split_bf16x3(const float* src, long long ld, int rows, const int* rows_dev, int k, void* dst, int order,
+                 cudaStream_t stream);
+// g.a / g.w are the SPLIT operands (bf16, pitches 3K); g.k = K (unsplit); out must be fp32
+int gemm_f32_split(const GemmArgs& g, cudaStream_t stream);
+
 }  // namespace ofx

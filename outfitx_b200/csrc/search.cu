@@ -1319,7 +1319,6 @@ int ofx_topk_search(const void* packed, const float* gallery_f32, int64_t n_rows
                 seed_finish_kernel<<<(n_query + 7) / 8, 256, 0, st>>>(queries, n_query, dim, metric, bm, nb_total, W.kcap, thr,
                     reinterpret_cast<const float*>(pk + L.stats), hq, hist);
                 OFX_LAUNCH_CHECK();
-                count_launch();
             }
         }
         if (W.kcap == 32) {

@@ -69,3 +69,39 @@ def test_gemm_rejects_bad_shapes():
     w = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(_lib.OfxError):
         _gemm(a, w)  # K % 64 != 0
+
+
+@pytest.mark.parametrize("m,n,k", [(17 * 64, 1536, 512), (1000, 512, 2048), (5, 1024, 1024), (4099, 2048, 1024), (300, 4608, 1536)])
+def test_fp32_operands_on_the_tensor_cores(m, n, k):
+    """ofx_gemm_f32_tc: fp32 A and W as bf16 hi / lo pieces, three products in one bf16 GEMM with K' = 3K.  Against
+    an fp64 matmul the error must be that of 16-bit mantissas (a few 1e-5 of the row scale), two orders below a
+    plain bf16 GEMM -- and bias / mish / in-place residual epilogues must work on it."""
+    from outfitx_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
+    bias = torch.randn(n, device="cuda", generator=g)
+    ws = torch.empty(L.ofx_gemm_f32_tc_workspace_bytes(m, n, k), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(act, res):
+        out = torch.empty(m, n, device="cuda") if res is None else res
+        _lib.check(L.ofx_gemm_f32_tc(a.data_ptr(), k, w.data_ptr(), k, m, n, k, bias.data_ptr(), act,
+                                     res.data_ptr() if res is not None else None, n, out.data_ptr(), n,
+                                     ws.data_ptr(), ws.numel(), st))
+        torch.cuda.synchronize()
+        return out
+
+    lin = (a.double() @ w.double().T + bias.double())
+    got = run(0, None)
+    err = (got.double() - lin).abs().max().item()
+    assert err <= 2e-4, err                                           # ~5 sigma of sqrt(K) products of ~2^-17 each
+    bf = (a.to(torch.bfloat16).double() @ w.to(torch.bfloat16).double().T + bias.double())
+    assert err * 30 < (bf - lin).abs().max().item()                    # the plain bf16 GEMM is >= 30x worse
+    torch.testing.assert_close(run(1, None).double(), torch.nn.functional.mish(lin), rtol=1e-4, atol=2e-4)
+    x = torch.randn(m, n, device="cuda", generator=g)
+    want = x.double() + lin
+    torch.testing.assert_close(run(0, x).double(), want, rtol=1e-4, atol=2e-4)
+    assert L.ofx_gemm_f32_tc(a.data_ptr(), k, w.data_ptr(), k, m, n, k, None, 0, None, 0, got.data_ptr(), n,
+                             ws.data_ptr(), 16, st) == -5
