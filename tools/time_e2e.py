@@ -34,3 +34,30 @@ t0 = time.perf_counter()
 for _ in range(20):
     lens64 = lens.to(torch.int64); off = torch.zeros(B + 1, dtype=torch.int64); torch.cumsum(lens64, 0, out=off[1:])
 print(f"host-side collate arithmetic: {(time.perf_counter()-t0)/20*1e3:.3f} ms")
+# where the packed step's time goes: the copies alone (same chunking, no scoring) and the scoring alone (chunks
+# already on the device)
+pipe = HostScoringPipeline(model, chunk=2048)
+pipe.score_packed(ir, tr, lens, host["text"], host["cand"])
+off = torch.zeros(B + 1, dtype=torch.int64); torch.cumsum(lens.to(torch.int64), 0, out=off[1:])
+def copies_only():
+    with torch.cuda.stream(pipe.copy_stream):
+        for i, lo in enumerate(range(0, B, 2048)):
+            hi = lo + 2048; s = i % pipe.n_slots; r0, r1 = int(off[lo]), int(off[hi])
+            pipe._stage_rows(s, "pimg", ir[r0:r1], 2048 * 16); pipe._stage_rows(s, "ptxt", tr[r0:r1], 2048 * 16)
+            pipe._stage(s, "text", host["text"][lo:hi]); pipe._stage(s, "cand", host["cand"][lo:hi])
+    pipe.copy_stream.synchronize()
+print(f"the four chunks' H2D copies alone: {t(copies_only):.2f} ms")
+dev_chunks = [dict(img=img[lo:lo + 2048].contiguous(), txt=txt[lo:lo + 2048].contiguous(), mask=mask[lo:lo + 2048].contiguous(),
+                   text=text[lo:lo + 2048].contiguous(), cand=cand[lo:lo + 2048].contiguous()) for lo in range(0, B, 2048)]
+def compute_only():
+    for c in dev_chunks:
+        enc = {"image_embeddings": c["img"], "text_embeddings": c["txt"]}
+        model.score_cp(outfit_mask=c["mask"], encoder_input_dict=enc)
+        model.score_fitb(outfit_mask=c["mask"], target_item_text_embedding=c["text"], candidate_item_embedding=c["cand"],
+                         encoder_input_dict=enc)
+print(f"scoring of four device-resident chunks of 2048 (eager launches): {t(compute_only):.2f} ms")
+enc = {"image_embeddings": img, "text_embeddings": txt}
+def compute_whole():
+    model.score_cp(outfit_mask=mask, encoder_input_dict=enc)
+    model.score_fitb(outfit_mask=mask, target_item_text_embedding=text, candidate_item_embedding=cand, encoder_input_dict=enc)
+print(f"scoring of the whole 8192-outfit batch: {t(compute_whole):.2f} ms")
