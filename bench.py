@@ -252,7 +252,7 @@ def cpu_cp_run(sd, img, txt, mask, text, cand, reps=2):
     emb[mask.numpy()] = 0.0
     emb = torch.from_numpy(emb)
     best, keep = float("inf"), None
-    for r in range(reps + 1):
+    for r in range(reps + 1):       # pass 0 is the warm-up (and the only pass when reps = 0: results only)
         t0 = time.perf_counter()
         probs = torch.sigmoid(port.cp(emb, mask).float())[:, 0]
         pred = dists = None
@@ -260,7 +260,7 @@ def cpu_cp_run(sd, img, txt, mask, text, cand, reps=2):
             q = port.cir(emb, mask, text)
             pred, dists = torch_port.fitb(q, cand)
         dt = time.perf_counter() - t0
-        if r > 0:
+        if r > 0 or reps == 0:
             best = min(best, dt)
         keep = (probs, pred, dists)
     return img.shape[0] / best, torch.get_num_threads(), keep[0], keep[1], keep[2]
@@ -287,7 +287,7 @@ def cpu_cir_sample(nq_s=256, n_s=200_000, reps=2):
         t0 = time.perf_counter()
         torch_port.search_cdist_topk(q, gal, k=TOPK)
         dt = time.perf_counter() - t0
-        if r > 0:
+        if r > 0 or reps == 0:
             best = min(best, dt)
     return nq_s * n_s / best  # (query, item) pairs per second
 
@@ -602,13 +602,15 @@ def main():
     # CPU baseline = the reference's stock-torch stack on the FIRST cpu_sample outfits of this very batch; the same
     # run verifies the GPU results (outside every timed region)
     cpu, verified, vhow = None, None, None
-    if rank == 0 and "cpu" not in skip and world == 1:
+    if rank == 0 and "cpu" not in skip:
+        # N > 1: rank 0 still checks its own results (one untimed pass of the port); the baseline is an N = 1 figure
         n = min(args.cpu_sample, B)
         v, threads, want_p, want_pred, want_d = cpu_cp_run(sd, host["img"][:n], host["txt"][:n], host["mask"][:n],
-                                                           host["text"][:n], host["cand"][:n])
-        cpu = {"value": v, "unit": "outfits/s", "cores": threads, "kind": "port",
-               "sample": f"the first {n} outfits of the 8192-outfit batch, CP + FITB, fp32, "
-                         "stock-torch port of the reference (oracle/torch_port.py)"}
+                                                           host["text"][:n], host["cand"][:n], reps=2 if world == 1 else 0)
+        if world == 1:
+            cpu = {"value": v, "unit": "outfits/s", "cores": threads, "kind": "port",
+                   "sample": f"the first {n} outfits of the 8192-outfit batch, CP + FITB, fp32, "
+                             "stock-torch port of the reference (oracle/torch_port.py)"}
         dprob = float((state["probs"][:n].cpu() - want_p).abs().max())
         agree = (state["fitb"][0][:n].cpu() == want_pred)
         dd = torch.sort(want_d, -1).values
@@ -636,7 +638,6 @@ def main():
                          "heads in fp32 on the CUDA cores",
                 "config": {"workload": "configs[1] (CP + FITB, 8192 outfits) with precision='fp32'"}}
         if cpu is not None:
-            n = min(args.cpu_sample, B)
             dp = float((st32["probs"][:n].cpu() - want_p).abs().max())
             same = bool((st32["fitb"][0][:n].cpu() == want_pred).all())
             fp32["verified"] = bool(dp <= 1e-4 and same)
