@@ -233,7 +233,9 @@ OFX_API int ofx_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw
                   int32_t k, const float* bias, int32_t act_mish, const float* residual,
                   int64_t ldr, void* out, int64_t ldo, int32_t out_f32, void* stream);
 
-/* ---- the fp32 mode's linear layer on the tensor cores: fp32 A (M,K) and W (N,K) are cut into bf16 hi / lo pieces
+/* ---- the fp32 mode's linear layer (the nn.Linear / F.linear calls inside the nn.TransformerEncoderLayer stack of
+ * src/models/outfit_x.py:32-45 and the CIR head :62-66 when the model runs without autocast) on the tensor cores:
+ * fp32 A (M,K) and W (N,K) are cut into bf16 hi / lo pieces
  * (16 mantissa bits) and  A.W^T ~= A_hi.W_hi^T + A_lo.W_hi^T + A_hi.W_lo^T  runs as ONE bf16 tcgen05 GEMM with K' = 3K
  * and fp32 accumulation (relative error ~2^-16 instead of bf16's 2^-8); out fp32.  What precision="fp32" of
  * ofx_encoder_forward uses for every nn.Linear (weights are split once by ofx_pack_weights).  K % 64 == 0,
