@@ -176,17 +176,10 @@ class HostScoringPipeline:
             if fitb:
                 out["pred"] = torch.empty(B, dtype=torch.int64).pin_memory()
         # host side of the collate, vectorised: row offsets, the padding mask and the chunk-local row id of every slot
-        off = torch.zeros(B + 1, dtype=torch.int64)
-        torch.cumsum(lens, 0, out=off[1:])
-        slot = torch.arange(max_items, dtype=torch.int64)
-        mask_h = self._pinned("mask", (B, max_items), torch.bool)
-        torch.ge(slot[None, :], lens[:, None], out=mask_h)
-        ids_h = self._pinned("ids", (B, max_items), torch.int32)
         plan = self._plan(B, taper=self.use_graphs)
-        starts = torch.tensor([lo for lo, _ in plan], dtype=torch.int64)
-        sizes = torch.tensor([hi - lo for lo, hi in plan], dtype=torch.int64)
-        chunk_base = off[starts].repeat_interleave(sizes)             # first row of each outfit's chunk
-        ids_h.copy_((off[:B, None] - chunk_base[:, None] + slot[None, :]).to(torch.int32))
+        mask_h = self._pinned("mask", (B, max_items), torch.bool)
+        ids_h = self._pinned("ids", (B, max_items), torch.int32)
+        off = packed_layout(lens, plan, max_items, mask_h, ids_h)
         cap_rows = self.chunk * max_items
         cur = torch.cuda.current_stream(self.dev)
         self.copy_stream.wait_stream(cur)
@@ -292,6 +285,24 @@ class HostScoringPipeline:
         cur.wait_stream(self.compute_stream)
         self.compute_stream.synchronize()
         return out
+
+
+def packed_layout(lengths: torch.Tensor, plan, max_items: int, mask_out: torch.Tensor, ids_out: torch.Tensor) -> torch.Tensor:
+    """Host arithmetic of the packed layout (CPU tensors only).  ``lengths (B,)`` int64, ``plan`` = [(lo, hi)] chunk
+    boundaries in outfits.  Fills ``mask_out (B, max_items)`` bool (True = padded slot, the reference's convention,
+    ``outfit_x_base_processor.py:70-81``) and ``ids_out (B, max_items)`` int32: slot (b, s) of a chunk reads row
+    ``off[b] - off[chunk start] + s`` of the chunk's staged rows (slots past the length are masked, whatever their id).
+    Returns ``off (B + 1,)``, the exclusive prefix sum of the lengths = each outfit's first row."""
+    B = lengths.numel()
+    off = torch.zeros(B + 1, dtype=torch.int64)
+    torch.cumsum(lengths, 0, out=off[1:])
+    slot = torch.arange(max_items, dtype=torch.int64)
+    torch.ge(slot[None, :], lengths[:, None], out=mask_out)
+    starts = torch.tensor([lo for lo, _ in plan], dtype=torch.int64)
+    sizes = torch.tensor([hi - lo for lo, hi in plan], dtype=torch.int64)
+    chunk_base = off[starts].repeat_interleave(sizes)             # first row of each outfit's chunk
+    ids_out.copy_((off[:B, None] - chunk_base[:, None] + slot[None, :]).to(torch.int32))
+    return off
 
 
 def pack_valid_rows(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor, outfit_mask: torch.Tensor):

@@ -90,3 +90,39 @@ def test_embedding_pickle_loader(tmp_path):
     assert index[101] == 6
     text = emb[:, 512:]            # polyvore_item_dataset.py:75: text embedding = second half
     assert text.shape == (8, 512)
+
+
+def test_packed_host_layout_arithmetic():
+    """The host side of HostScoringPipeline.score_packed (pure CPU): mask, chunk-local row ids and offsets of a
+    ragged batch, and the round trip padded -> packed -> gathered-by-ids == padded (valid slots)."""
+    import numpy as np
+    import torch
+    from outfitx_b200.pipeline import pack_valid_rows, packed_layout
+    rng = np.random.Generator(np.random.PCG64(7))
+    B, L, d = 37, 16, 8
+    lengths = torch.from_numpy(rng.integers(0, L + 1, size=B)).to(torch.int64)
+    lengths[0], lengths[1] = 0, L                                # the edge cases
+    mask = torch.arange(L)[None, :] >= lengths[:, None]          # left-aligned valid items
+    img = torch.from_numpy(rng.standard_normal((B, L, d)).astype(np.float32))
+    txt = torch.from_numpy(rng.standard_normal((B, L, d)).astype(np.float32))
+    ir, tr, lens = pack_valid_rows(img, txt, mask)
+    assert torch.equal(lens.to(torch.int64), lengths) and ir.shape == (int(lengths.sum()), d)
+    plan = [(0, 10), (10, 11), (11, 30), (30, 37)]                # ragged chunks
+    mask_out = torch.empty(B, L, dtype=torch.bool)
+    ids = torch.empty(B, L, dtype=torch.int32)
+    off = packed_layout(lengths, plan, L, mask_out, ids)
+    assert torch.equal(mask_out, mask)
+    assert off[0] == 0 and off[-1] == lengths.sum() and torch.equal(off[1:] - off[:-1], lengths)
+    for lo, hi in plan:
+        rows_i, rows_t = ir[int(off[lo]):int(off[hi])], tr[int(off[lo]):int(off[hi])]      # what the chunk stages
+        for b in range(lo, hi):
+            n = int(lengths[b])
+            sel = ids[b, :n].long()
+            assert n == 0 or (int(sel.min()) >= 0 and int(sel.max()) < rows_i.shape[0])
+            assert torch.equal(rows_i[sel], img[b, :n]) and torch.equal(rows_t[sel], txt[b, :n])
+    # a mask that is not left-aligned keeps the slot order of the valid items
+    m2 = mask.clone(); m2[5] = torch.tensor([1, 0, 1, 1, 0, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0], dtype=torch.bool)
+    ir2, _, lens2 = pack_valid_rows(img, txt, m2)
+    o2 = int(lens2[:5].sum())
+    n5 = int((~m2[5]).sum())
+    assert n5 == 5 and int(lens2[5]) == n5 and torch.equal(ir2[o2:o2 + n5], img[5][~m2[5]])
