@@ -17,6 +17,7 @@ ap.add_argument("--batch", type=int, default=8192)
 ap.add_argument("--skip-cp", action="store_true")
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--skip-cir", action="store_true")
+ap.add_argument("--k", type=int, default=10)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 if not a.skip_cp:
@@ -38,12 +39,12 @@ if not a.skip_cir:
     gal = Gallery.build(rows)
     q = torch.randn(a.queries, 1024, device=dev, generator=torch.Generator(device=dev).manual_seed(6)) * 0.05
     for _ in range(2):
-        local_search(q, gal, 10, "l2", True)
+        local_search(q, gal, a.k, "l2", True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.reps):
-        local_search(q, gal, 10, "l2", True)
+        local_search(q, gal, a.k, "l2", True)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.reps
