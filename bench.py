@@ -10,7 +10,7 @@ collective).  The same line carries one object per remaining config, each with i
 `cpu_baseline` and a `verified` flag computed OUTSIDE the timed region against an independent check:
 
   cir    configs[3]: 8192 queries, exact top-10 over a 10 M-item gallery sharded across the N GPUs with one
-         NCCL all-gather (strong scaling); verified against the exhaustive fp64 scan of 16 queries.
+         NCCL all-gather (strong scaling); verified against the exhaustive fp64 scan of 64 queries.
   cir3   configs[2] (N = 1 only): 4096 ENCODER-PRODUCED queries (d_model 1024 CIR forward) + exact top-10 over
          1 M items, embed + search timed together.
   large  configs[4] (N = 1 only): large-encoder CP sweep, d_model 1024, 16 items, batch 256 .. 32768.
@@ -405,7 +405,7 @@ def bench_search(ctx, args, n_rows, queries, k_steps, label, peak_kind, embed=No
         e2e = {"value": nq * k_steps / (e2e_ms * 1e-3), "unit": "queries/s",
                "h2d_bytes_per_step": q_host.numel() * 4, "d2h_bytes_per_step": idx_host.numel() * 8}
 
-    ok, n_chk = exhaustive_check(state["q"], gal, state["res"][0], state["res"][1], TOPK, 16, dist_ok, dev)
+    ok, n_chk = exhaustive_check(state["q"], gal, state["res"][0], state["res"][1], TOPK, 64, dist_ok, dev)
     peak = pk[peak_kind]
     traffic, tsrc = ncu_traffic(f"search_sweep_{n_rows}") if world == 1 else (None, None)
     out = {
