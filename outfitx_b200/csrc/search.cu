@@ -438,11 +438,11 @@ struct EpiTopK {
 // the whole gallery -- a valid starting threshold for the top-m lists of the main sweep.  The sample is split
 // into as many segments as there are idle CTA pairs per query group (2 at 8192 queries, 4 at 4096): the units
 // only write their maxima, seed_finish_kernel takes the m-th largest of the POOL (64 -> 128 blocks moves the
-// bound from the 0.54 % to the 0.22 % quantile at the same wall time).  Unlike running
-// the real top-k epilogue over a sample (the previous warm-up: 1.15 ms at 8192 queries, dominated by
-// divergent list insertions while the lists are cold) this is one running maximum per thread and a
-// warp-uniform selection at the end: ~60 us for 64 blocks, and with NB = 2 m the bound (the median of
-// maxima of 128 samples = the 0.54 % quantile) is tighter than the exact m-th best of 4096 rows (0.78 %).
+// bound from the 0.54 % to the 0.22 % quantile at the same wall time).  Unlike running the real top-k epilogue
+// over a sample (the first warm-up: 1.15 ms at 8192 queries, dominated by list insertions into cold lists) this is
+// one running maximum per thread per block: ~0.2 ms for 64 blocks per segment, and with NB = 2 m per segment the
+// bound (the median of maxima of 128 samples = the 0.54 % quantile) is already tighter than the exact m-th best of
+// 4096 rows (0.78 %).
 // ---------------------------------------------------------------------------------------
 template <int NBMAX>
 struct EpiBlockMax {
