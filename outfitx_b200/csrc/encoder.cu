@@ -130,10 +130,12 @@ static WsLayout make_ws(const ofx_shape* s, int batch) {
     W.owner = take(t * 4);
     W.x = take(t * dm * 4);
     W.h = take(t * dm * esz);
-    W.big = take(t * W.big_ld * esz);
+    // fp32 precision: `big` / `u0` also hold the hidden activation as bf16 pieces (3 x fp bf16 per row, gemm.h)
+    const size_t big_row = s->precision == OFX_PREC_FP32 ? (W.big_ld * esz > 6 * fp ? W.big_ld * esz : 6 * fp) : W.big_ld * esz;
+    W.big = take(t * big_row);
     W.q0 = take(static_cast<size_t>(batch) * dm * esz);
     W.a0 = take(static_cast<size_t>(batch) * dm * esz);
-    W.u0 = take(static_cast<size_t>(batch) * fp * esz);
+    W.u0 = take(static_cast<size_t>(batch) * fp * (s->precision == OFX_PREC_FP32 ? 6 : esz));
     // the fused FFN block's exchange ring + counters (bf16 path, d_model 512)
     W.ffn_bytes = (s->precision == OFX_PREC_BF16 && ffn_block_supported(s->d_model, static_cast<int>(fp))) ? ffn_block_workspace_bytes() : 0;
     W.ffn = take(W.ffn_bytes);
@@ -198,17 +200,35 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
     // bf16 hi / lo pieces and multiplied with the pre-split weights on the same tensor-core pipeline (gemm.h)
     uint8_t* split_a = ws + W.split;
     const bool tc32 = sizeof(T) == 4 && L.s_qkv && fp32_tc_enabled();
-    auto mm = [&](const GemmArgs& g, const uint8_t* w_split) -> int {
+    // a_pre: the activation operand already lies somewhere as pieces (layernorm_split3 / a piece-output GEMM wrote it);
+    // piece_out: write the result as the pieces of the NEXT GEMM's operand instead of fp32
+    auto mm = [&](const GemmArgs& g, const uint8_t* w_split, const void* a_pre = nullptr, void* piece_out = nullptr) -> int {
         if constexpr (sizeof(T) == 4) {
             if (tc32) {
-                OFX_TRY(split_bf16x3(static_cast<const float*>(g.a), g.lda, g.m, g.m_dev, g.k, split_a, kSplitA, st));
+                if (!a_pre) {
+                    OFX_TRY(split_bf16x3(static_cast<const float*>(g.a), g.lda, g.m, g.m_dev, g.k, split_a, kSplitA, st));
+                    a_pre = split_a;
+                }
                 GemmArgs t = g;
-                t.a = split_a; t.lda = 3LL * g.k; t.w = w_split; t.ldw = 3LL * g.k; t.out_f32 = 1;
+                t.a = a_pre; t.lda = 3LL * g.k; t.w = w_split; t.ldw = 3LL * g.k; t.out_f32 = 1;
+                if (piece_out) { t.out = piece_out; t.ldo = 3LL * g.n; t.out_f32 = 2; }
                 return gemm_f32_split(t, st);
             }
         }
-        (void)w_split;
+        (void)w_split; (void)a_pre; (void)piece_out;
         return gemm<T>(g, st);
+    };
+    // LayerNorm in front of a linear layer: h = LN(x); in the fp32 tensor-core mode the pieces of the GEMM operand are
+    // written straight into split_a instead (*pre = where they are)
+    auto ln_mm = [&](int rows, const int* rows_dev, const float* w, const float* b, const void** pre) -> int {
+        *pre = nullptr;
+        if constexpr (sizeof(T) == 4) {
+            if (tc32) {
+                *pre = split_a;
+                return layernorm_split3(x, rows, rows_dev, dm, w, b, split_a, st);
+            }
+        }
+        return layernorm<T>(x, rows, rows_dev, dm, w, b, h, st);
     };
     const bool fused_ffn = sizeof(T) == 2 && ffn_block_supported(dm, fp) && fused_ffn_enabled();
 
@@ -230,15 +250,16 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
     for (int l = 0; l < L.nl; ++l) {
         const bool last = l == L.nl - 1;
         // with the fused FFN block the previous layer has already emitted h = norm1_l(x)
+        const void* pre1 = nullptr;      // pieces of norm1's output, when the LayerNorm wrote them itself
         if (l > 0 && !(fused_ffn && ffn_emits_ln()))
-            OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln1w), lf(l, L.ln1b), h, st));
+            OFX_TRY(ln_mm(W.t_max, n_tok, lf(l, L.ln1w), lf(l, L.ln1b), &pre1));
         AttnArgs at{};
         at.batch = B; at.n_head = s->n_head; at.off = off; at.max_s = s->max_items + 1;
         at.max_rows = W.t_max; at.n_tok = n_tok; at.owner = owner;
         if (!last) {
             // dense layer over every valid token
             GemmArgs g{h, dm, lw(l, L.w_qkv), dm, W.t_max, n_tok, 3 * dm, dm, lf(l, L.b_qkv), 0, nullptr, 0, big, 3 * dm, 0};
-            OFX_TRY(mm(g, lw(l, L.s_qkv)));
+            OFX_TRY(mm(g, lw(l, L.s_qkv), pre1));
             at.row0_only = 0;
             at.q = big; at.k = big + dm; at.v = big + 2 * dm; at.ldq = at.ldk = at.ldv = 3 * dm;
             at.out = h; at.ldo = dm;
@@ -252,20 +273,22 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
                 fa.workspace = ws + W.ffn; fa.workspace_bytes = W.ffn_bytes;
                 OFX_TRY(ffn_block_bf16(fa, st));
             } else {
-                OFX_TRY(layernorm<T>(x, W.t_max, n_tok, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
+                const void* pre2 = nullptr;
+                OFX_TRY(ln_mm(W.t_max, n_tok, lf(l, L.ln2w), lf(l, L.ln2b), &pre2));
                 GemmArgs g1{h, dm, lw(l, L.w_1), dm, W.t_max, n_tok, fp, dm, lf(l, L.b_1), 1, nullptr, 0, big, fp, 0};
-                OFX_TRY(mm(g1, lw(l, L.s_1)));
+                OFX_TRY(mm(g1, lw(l, L.s_1), pre2, tc32 ? big : nullptr));          // fp32 tc: hidden as pieces
                 GemmArgs g2{big, fp, lw(l, L.w_2), fp, W.t_max, n_tok, dm, fp, lf(l, L.b_2), 0, x, dm, x, dm, 1};
-                OFX_TRY(mm(g2, lw(l, L.s_2)));
+                OFX_TRY(mm(g2, lw(l, L.s_2), tc32 ? big : nullptr));
             }
         } else {
             // last layer: K,V for every token, everything else for the prefix row only
             const T* w_in = reinterpret_cast<const T*>(lw(l, L.w_qkv));
             GemmArgs gkv{h, dm, w_in + static_cast<size_t>(dm) * dm, dm, W.t_max, n_tok, 2 * dm, dm,
                          lf(l, L.b_qkv) + dm, 0, nullptr, 0, big, 2 * dm, 0};
-            OFX_TRY(mm(gkv, lw(l, L.s_qkv) + static_cast<size_t>(dm) * 3 * dm * 2));     // rows dm.. of the split W_qkv
+            OFX_TRY(mm(gkv, lw(l, L.s_qkv) + static_cast<size_t>(dm) * 3 * dm * 2, pre1));     // rows dm.. of the split W_qkv
             GemmArgs gq{h, dm, w_in, dm, B, nullptr, dm, dm, lf(l, L.b_qkv), 0, nullptr, 0, q0, dm, 0};
-            OFX_TRY(mm(gq, lw(l, L.s_qkv)));
+            // without pre1 (single-layer model) the K/V GEMM above has just split all of h into split_a: rows [0, B) of it
+            OFX_TRY(mm(gq, lw(l, L.s_qkv), tc32 ? static_cast<const void*>(split_a) : nullptr));
             at.row0_only = 1;
             at.q = q0; at.ldq = dm; at.k = big; at.v = big + dm; at.ldk = at.ldv = 2 * dm;
             at.out = a0; at.ldo = dm;
@@ -278,11 +301,12 @@ static int forward(const ofx_shape* s, const uint8_t* wts, const ofx_forward_arg
                 fa.workspace = ws + W.ffn; fa.workspace_bytes = W.ffn_bytes;
                 OFX_TRY(ffn_block_bf16(fa, st));
             } else {
-                OFX_TRY(layernorm<T>(x, B, nullptr, dm, lf(l, L.ln2w), lf(l, L.ln2b), h, st));
+                const void* pre2 = nullptr;
+                OFX_TRY(ln_mm(B, nullptr, lf(l, L.ln2w), lf(l, L.ln2b), &pre2));
                 GemmArgs g1{h, dm, lw(l, L.w_1), dm, B, nullptr, fp, dm, lf(l, L.b_1), 1, nullptr, 0, u0, fp, 0};
-                OFX_TRY(mm(g1, lw(l, L.s_1)));
+                OFX_TRY(mm(g1, lw(l, L.s_1), pre2, tc32 ? u0 : nullptr));
                 GemmArgs g2{u0, fp, lw(l, L.w_2), fp, B, nullptr, dm, fp, lf(l, L.b_2), 0, x, dm, x, dm, 1};
-                OFX_TRY(mm(g2, lw(l, L.s_2)));
+                OFX_TRY(mm(g2, lw(l, L.s_2), tc32 ? u0 : nullptr));
             }
         }
     }

@@ -321,6 +321,68 @@ int layernorm(const float* x, int rows, const int* rows_dev, int dm, const float
     OFX_LAUNCH_CHECK();
     return OFX_OK;
 }
+// LayerNorm whose output is the activation operand of a split-bf16 GEMM (precision fp32 on the tensor cores, gemm.h):
+// the normalised fp32 row is written as its bf16 pieces [hi | lo | hi], row pitch 3 DM -- same arithmetic as
+// ln_store<DM, float> followed by split3_kernel, one pass instead of two.
+template <int DM>
+__global__ void __launch_bounds__(256)
+layernorm_split3_kernel(const float* __restrict__ x, int rows, const int* __restrict__ rows_dev,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
+    constexpr int NV = DM / 128;
+    const int n = rows_dev ? min(*rows_dev, rows) : rows;
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + row * DM + i * 128 + lane * 4);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+    const float mu = warp_sum(s) * (1.f / DM);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+        q += a * a + b * b + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / DM) + 1e-5f);
+    __nv_bfloat16* o = out + row * (3 * DM);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int e = i * 128 + lane * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + e));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + e));
+        const float y[4] = {(v[i].x - mu) * rstd * g.x + b.x, (v[i].y - mu) * rstd * g.y + b.y,
+                            (v[i].z - mu) * rstd * g.z + b.z, (v[i].w - mu) * rstd * g.w + b.w};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2bfloat16_rn(y[j]);
+            lo[j] = __float2bfloat16_rn(y[j] - __bfloat162float(hi[j]));
+        }
+        const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
+        *reinterpret_cast<uint2*>(o + e) = h2;
+        *reinterpret_cast<uint2*>(o + DM + e) = l2;
+        *reinterpret_cast<uint2*>(o + 2 * DM + e) = h2;
+    }
+}
+
+int layernorm_split3(const float* x, int rows, const int* rows_dev, int dm, const float* gamma, const float* beta,
+                     void* out, cudaStream_t stream) {
+    if (rows <= 0) return OFX_OK;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+    switch (dm) {
+        case 512: layernorm_split3_kernel<512><<<grid, 256, 0, stream>>>(x, rows, rows_dev, gamma, beta, o); break;
+        case 1024: layernorm_split3_kernel<1024><<<grid, 256, 0, stream>>>(x, rows, rows_dev, gamma, beta, o); break;
+        case 1536: layernorm_split3_kernel<1536><<<grid, 256, 0, stream>>>(x, rows, rows_dev, gamma, beta, o); break;
+        default: return fail(OFX_E_SHAPE, "d_model %d not in {512,1024,1536}", dm);
+    }
+    OFX_LAUNCH_CHECK();
+    return OFX_OK;
+}
+
 template int layernorm<float>(const float*, int, const int*, int, const float*, const float*, float*, cudaStream_t);
 template int layernorm<__nv_bfloat16>(const float*, int, const int*, int, const float*, const float*, __nv_bfloat16*, cudaStream_t);
 

@@ -69,6 +69,9 @@ int fuse_rows(const float* img, const float* txt, long long rows, int dpm, int m
 template <class T> int assemble(const AssembleArgs& a, int dm, float* x, T* h, cudaStream_t stream);
 template <class T> int layernorm(const float* x, int rows, const int* rows_dev, int dm, const float* gamma,
                                  const float* beta, T* out, cudaStream_t stream);
+// LayerNorm written as the bf16 pieces [hi | lo | hi] (row pitch 3 dm) of a split-bf16 GEMM's activation operand
+int layernorm_split3(const float* x, int rows, const int* rows_dev, int dm, const float* gamma, const float* beta,
+                     void* out, cudaStream_t stream);
 template <class T> int cast_rows(const float* in, long long n, T* out, cudaStream_t stream);
 template <class T> int attention(const AttnArgs& a, int head_dim, cudaStream_t stream);
 int cp_head(const float* x0, int batch, int dm, const float* w, const float* bias, float* logits,

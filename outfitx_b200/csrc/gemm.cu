@@ -146,7 +146,23 @@ struct EpiLinear {
                     v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
                     if (p.act_mish) { v.x = mish_fast(v.x); v.y = mish_fast(v.y); v.z = mish_fast(v.z); v.w = mish_fast(v.w); }
                     if (resp) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-                    if (p.out_f32) {
+                    if (p.out_f32 == 2) {
+                        // fp32 mode: the result is the NEXT split GEMM's activation operand -- write its bf16 pieces
+                        // [hi | lo | hi] (row pitch ldo = 3 N) instead of the fp32 value (gemm.h)
+                        const float f[4] = {v.x, v.y, v.z, v.w};
+                        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            hi[j] = __float2bfloat16_rn(f[j]);
+                            lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
+                        }
+                        __nv_bfloat16* o = outh + sl * 32 + i * ldo4;
+                        const long long nn = p.ldo / 3;
+                        const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
+                        *reinterpret_cast<uint2*>(o) = h2;
+                        *reinterpret_cast<uint2*>(o + nn) = l2;
+                        *reinterpret_cast<uint2*>(o + 2 * nn) = h2;
+                    } else if (p.out_f32) {
                         *reinterpret_cast<float4*>(outf + sl * 32 + i * ldo4) = v;
                     } else {
                         __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -478,7 +494,9 @@ int split_bf16x3(const float* src, long long ld, int rows, const int* rows_dev, 
 }
 
 int gemm_f32_split(const GemmArgs& g, cudaStream_t stream) {
-    if (!g.out_f32) return fail(OFX_E_ARG, "gemm_f32_split: the output must be fp32");
+    if (!g.out_f32) return fail(OFX_E_ARG, "gemm_f32_split: the output must be fp32 (1) or its bf16 pieces (2)");
+    if (g.out_f32 == 2 && (g.residual || g.ldo != 3LL * g.n))
+        return fail(OFX_E_ARG, "gemm_f32_split: piece output needs ldo == 3 N and no residual");
     GemmArgs t = g;
     t.k = 3 * g.k;
     return gemm_bf16(t, stream);

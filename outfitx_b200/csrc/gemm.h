@@ -31,7 +31,9 @@ int gemm_f32(const GemmArgs& g, cudaStream_t stream);
 constexpr int kSplitA = 0, kSplitW = 1;
 int split_bf16x3(const float* src, long long ld, int rows, const int* rows_dev, int k, void* dst, int order,
                  cudaStream_t stream);
-// g.a / g.w are the SPLIT operands (bf16, pitches 3K); g.k = K (unsplit); out must be fp32
+// g.a / g.w are the SPLIT operands (bf16, pitches 3K); g.k = K (unsplit); out_f32 = 1: fp32 output;
+// out_f32 = 2: the output is written as the [hi | lo | hi] pieces of the next split GEMM's activation operand
+// (bf16, ldo = 3 N, no residual)
 int gemm_f32_split(const GemmArgs& g, cudaStream_t stream);
 
 }  // namespace ofx
